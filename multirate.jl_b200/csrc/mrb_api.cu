@@ -1,0 +1,743 @@
+// mrb_api.cu -- the C-ABI of include/mrb.h: handle, host sequencing, kernel dispatch.
+// Compiled for sm_100a only.  There is no CPU compute path in this library.
+#include "../../include/mrb.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "mrb_kernels.cuh"
+#include "mrb_seq.h"
+#include "mrb_tiled.cuh"
+
+using namespace mrb;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int32_t fail(int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? MRB_ERR_NO_DEVICE \
+                                                                                      : MRB_ERR_CUDA,    \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);    \
+    } while (0)
+
+static size_t dsize(int d) { return d == MRB_F32 ? 4 : d == MRB_F64 ? 8 : d == MRB_C64 ? 8 : 16; }
+static bool is_complex(int d) { return d == MRB_C64 || d == MRB_C128; }
+static bool is_double(int d) { return d == MRB_F64 || d == MRB_C128; }
+// promote_type(Th, Tx), src/Filters.jl:476,522,581
+static int promote(int th, int tx) {
+    const bool dbl = th == MRB_F64 || is_double(tx);
+    return is_complex(tx) ? (dbl ? MRB_C128 : MRB_C64) : (dbl ? MRB_F64 : MRB_F32);
+}
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct SchedSlot {            // pinned host staging + device copy of one table-schedule sub-chunk
+    int64_t *h_n = nullptr, *d_n = nullptr;
+    int32_t *h_phi = nullptr, *d_phi = nullptr;
+    double *h_a = nullptr, *d_a = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool pending = false;
+};
+
+struct mrb_filter {
+    int kind, th, tx, ty, device;
+    int64_t hLen, L, M, Nphi, T, H, nch;
+    int polyorder;
+    double rate, delta;
+    std::vector<double> bank, dbank;   // [Nphi][T] row phi = pfb[:, phi]; exact values of the Th taps
+    std::vector<double> pnfb;          // [T][order+1]
+    // carried state, 1-based like the reference
+    int64_t phiIdx, deficit, xIdx;
+    double acc, alpha;
+    // device
+    void *d_bank = nullptr, *d_dbank = nullptr;   // compute real type R
+    double *d_pnfb = nullptr;
+    void *d_hist[2] = {nullptr, nullptr};
+    int cur = 0;
+    SchedSlot slot[2];
+    int64_t sched_cap = 0;
+    void *d_taptab = nullptr;          // farrow: R[sched_cap][T]
+    // host-call staging
+    void *d_xs = nullptr, *d_ys = nullptr;
+    size_t xs_bytes = 0, ys_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    TiledPlan tiled;                   // fast-path resources (mrb_tiled.cuh)
+    int policy = 0;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // one pair per timed mrb_filt
+    const char *last_kernel = "none";
+    int64_t launches = 0;
+};
+
+static const int64_t kSchedChunk = 1 << 16;   // outputs per table-schedule sub-chunk
+
+static void free_device(mrb_filter *f) {
+    if (f->device < 0) return;
+    cudaSetDevice(f->device);
+    cudaFree(f->d_bank); cudaFree(f->d_dbank); cudaFree(f->d_pnfb);
+    cudaFree(f->d_hist[0]); cudaFree(f->d_hist[1]);
+    for (auto &s : f->slot) {
+        cudaFreeHost(s.h_n); cudaFreeHost(s.h_phi); cudaFreeHost(s.h_a);
+        cudaFree(s.d_n); cudaFree(s.d_phi); cudaFree(s.d_a);
+        if (s.ev) cudaEventDestroy(s.ev);
+    }
+    cudaFree(f->d_taptab); cudaFree(f->d_xs); cudaFree(f->d_ys);
+    tiled_release(f->tiled);
+    for (auto &p : f->tev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (f->own_stream) cudaStreamDestroy(f->own_stream);
+}
+
+// src/Filters.jl:284-298, written phase-major: bank[phi*T + (T-1-r)] = h[r*Nphi + phi]
+static void make_bank(const std::vector<double> &h, int64_t Nphi, int64_t T, std::vector<double> &bank) {
+    bank.assign((size_t)(Nphi * T), 0.0);
+    int64_t hIdx = 0;
+    const int64_t hLen = (int64_t)h.size();
+    for (int64_t row = T - 1; row >= 0; --row)
+        for (int64_t col = 0; col < Nphi; ++col, ++hIdx) bank[col * T + row] = hIdx < hLen ? h[hIdx] : 0.0;
+}
+
+template <typename R>
+static cudaError_t upload_real(const std::vector<double> &src, void **dst) {
+    std::vector<R> tmp(src.size());
+    for (size_t i = 0; i < src.size(); ++i) tmp[i] = (R)src[i];
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(tmp.size(), 1) * sizeof(R));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(R), cudaMemcpyHostToDevice);
+}
+
+static void init_state(mrb_filter *f) {
+    f->phiIdx = 1; f->deficit = 1; f->xIdx = 1; f->acc = 1.0; f->alpha = 0.0;
+}
+
+extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
+    if (!d || !out) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (!d->h || d->h_len < 1) return fail(MRB_ERR_BAD_ARGUMENT, "h must hold at least one tap");
+    if (d->tap_dtype != MRB_F32 && d->tap_dtype != MRB_F64)
+        return fail(MRB_ERR_BAD_ARGUMENT, "tap dtype must be Float32 or Float64");
+    if (d->sample_dtype < MRB_F32 || d->sample_dtype > MRB_C128) return fail(MRB_ERR_BAD_ARGUMENT, "bad sample dtype");
+    if (d->n_channels < 1) return fail(MRB_ERR_BAD_ARGUMENT, "n_channels must be >= 1");
+
+    std::unique_ptr<mrb_filter> f(new mrb_filter());
+    f->th = d->tap_dtype; f->tx = d->sample_dtype; f->ty = promote(f->th, f->tx);
+    f->device = d->device; f->nch = d->n_channels; f->hLen = d->h_len;
+    f->rate = 0.0; f->delta = 0.0; f->polyorder = -1; f->L = 1; f->M = 1;
+
+    std::vector<double> h((size_t)d->h_len);
+    for (int64_t i = 0; i < d->h_len; ++i)
+        h[i] = f->th == MRB_F32 ? (double)static_cast<const float *>(d->h)[i] : static_cast<const double *>(d->h)[i];
+
+    int kind = d->kind;
+    if (d->rate != 0.0 || kind == MRB_ARBITRARY || kind == MRB_FARROW) {
+        // FIRFilter(h, rate, Nphi[, polyorder]) -- src/Filters.jl:183-198
+        if (!(d->rate > 0.0)) return fail(MRB_ERR_BAD_ARGUMENT, "rate must be greater than 0");
+        const int want = d->poly_order >= 0 ? MRB_FARROW : MRB_ARBITRARY;
+        if (kind == MRB_KIND_AUTO) kind = want;
+        if (kind != want) return fail(MRB_ERR_BAD_ARGUMENT, "kind does not agree with rate / poly_order");
+        f->Nphi = d->n_phi > 0 ? d->n_phi : 32;
+        f->rate = d->rate;
+        f->delta = (double)f->Nphi / d->rate;                          // :113,142
+        f->T = ceil_div(d->h_len, f->Nphi);
+        make_bank(h, f->Nphi, f->T, f->bank);
+        if (kind == MRB_ARBITRARY) {
+            std::vector<double> dh(h.size(), 0.0);                     // dh = [diff(h); 0] in Th arithmetic, :106
+            for (size_t i = 0; i + 1 < h.size(); ++i)
+                dh[i] = f->th == MRB_F32 ? (double)((float)h[i + 1] - (float)h[i]) : h[i + 1] - h[i];
+            make_bank(dh, f->Nphi, f->T, f->dbank);
+        } else {
+            if (!d->poly_coeffs) return fail(MRB_ERR_BAD_ARGUMENT, "farrow needs host-fitted poly_coeffs");
+            f->polyorder = d->poly_order;
+            f->pnfb.assign(d->poly_coeffs, d->poly_coeffs + f->T * (d->poly_order + 1));
+        }
+    } else {
+        // FIRFilter(h, ratio) -- src/Filters.jl:158-180
+        int64_t L = d->interpolation, M = d->decimation;
+        if (L < 1 || M < 1) return fail(MRB_ERR_BAD_ARGUMENT, "interpolation and decimation must be >= 1");
+        int64_t a = L, b = M;
+        while (b) { int64_t t = a % b; a = b; b = t; }
+        L /= a; M /= a;                                                 // Julia Rational is always reduced
+        const int want = (L == 1 && M == 1) ? MRB_STANDARD : L == 1 ? MRB_DECIMATOR : M == 1 ? MRB_INTERPOLATOR : MRB_RATIONAL;
+        if (kind == MRB_KIND_AUTO) kind = want;
+        if (kind != want) return fail(MRB_ERR_BAD_ARGUMENT, "kind does not agree with the resampling ratio");
+        f->L = L; f->M = M;
+        if (kind == MRB_STANDARD || kind == MRB_DECIMATOR) {
+            f->Nphi = 1; f->T = d->h_len;                               // flipud(h), :21,:53
+            f->bank.resize(h.size());
+            for (size_t i = 0; i < h.size(); ++i) f->bank[i] = h[h.size() - 1 - i];
+        } else {
+            f->Nphi = L; f->T = ceil_div(d->h_len, L);                  // taps2pfb(h, L), :36,:73
+            make_bank(h, f->Nphi, f->T, f->bank);
+        }
+    }
+    f->kind = kind;
+    f->H = f->T - 1;                                                    // :165,168,171,174,186,195
+    init_state(f.get());
+
+    if (f->device >= 0) {
+        int ndev = 0;
+        CU(cudaGetDeviceCount(&ndev));
+        if (f->device >= ndev) return fail(MRB_ERR_NO_DEVICE, "device %d not present (%d devices)", f->device, ndev);
+        CU(cudaSetDevice(f->device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, f->device));
+        if (prop.major != 10)
+            return fail(MRB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library holds sm_100a code only", f->device,
+                        prop.major, prop.minor);
+        const bool dbl = is_double(f->ty);
+        CU(dbl ? upload_real<double>(f->bank, &f->d_bank) : upload_real<float>(f->bank, &f->d_bank));
+        if (kind == MRB_ARBITRARY) CU(dbl ? upload_real<double>(f->dbank, &f->d_dbank) : upload_real<float>(f->dbank, &f->d_dbank));
+        if (kind == MRB_FARROW) {
+            CU(cudaMalloc(&f->d_pnfb, f->pnfb.size() * sizeof(double)));
+            CU(cudaMemcpy(f->d_pnfb, f->pnfb.data(), f->pnfb.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        const size_t hb = std::max<size_t>((size_t)(f->H * f->nch) * dsize(f->tx), 16);
+        for (int i = 0; i < 2; ++i) { CU(cudaMalloc(&f->d_hist[i], hb)); CU(cudaMemset(f->d_hist[i], 0, hb)); }
+        CU(cudaStreamCreateWithFlags(&f->own_stream, cudaStreamNonBlocking));
+        int32_t rc = tiled_prepare(f->tiled, kind, f->tx, f->ty, f->L, f->M, f->Nphi, f->T, f->bank, f->dbank, prop);
+        if (rc != 0) return fail(MRB_ERR_CUDA, "tiled_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
+        CU(cudaDeviceSynchronize());
+    }
+    *out = f.release();
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_destroy(mrb_filter *f) {
+    if (!f) return MRB_OK;
+    free_device(f);
+    delete f;
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_get_info(const mrb_filter *f, mrb_info *o) {
+    if (!f || !o) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    o->kind = f->kind; o->tap_dtype = f->th; o->sample_dtype = f->tx; o->out_dtype = f->ty; o->device = f->device;
+    o->n_phi = (int32_t)f->Nphi; o->poly_order = f->polyorder;
+    o->taps_per_phase = f->T; o->history_len = f->H; o->h_len = f->hLen;
+    o->interpolation = f->L; o->decimation = f->M; o->n_channels = f->nch; o->rate = f->rate;
+    return MRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sequencing
+// ------------------------------------------------------------------------------------------
+static bool is_table_kind(const mrb_filter *f) { return f->kind == MRB_ARBITRARY || f->kind == MRB_FARROW; }
+
+extern "C" int32_t mrb_outputlength(const mrb_filter *f, int64_t n_in, int64_t *n_out) {
+    if (!f || !n_out || n_in < 0) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    switch (f->kind) {
+    case MRB_STANDARD: *n_out = n_in; break;                                              // :359-361
+    case MRB_INTERPOLATOR: *n_out = f->L * n_in; break;                                   // :363-365
+    case MRB_DECIMATOR:                                                                   // :367-369
+    case MRB_RATIONAL:                                                                    // :371-373 -> :352-357
+        *n_out = (int64_t)std::ceil((double)((n_in - f->deficit + 1) * f->L - f->phiIdx + 1) / (double)f->M);
+        break;
+    default: *n_out = (int64_t)std::ceil((double)(n_in - f->deficit + 1) * f->rate); break;   // :375-381
+    }
+    return MRB_OK;
+}
+
+// Exact replay for the table kinds.  Fills (n 0-based, phi 0-based / phase, alpha) when the vectors are given.
+static int64_t replay_table(const mrb_filter *f, int64_t n_in, mrb_state *end, std::vector<int64_t> *vn,
+                            std::vector<int32_t> *vphi, std::vector<double> *va) {
+    mrb_state s{f->phiIdx, f->deficit, f->xIdx, f->acc, f->alpha};
+    int64_t count = 0;
+    if (n_in < s.input_deficit) {                                       // :705-709, :805-809
+        s.input_deficit -= n_in;
+    } else {
+        ArbState a{s.phi_accumulator, s.input_deficit};                 // xIdx = inputDeficit, :715,:812
+        while (a.xIdx <= n_in) {
+            if (vn) vn->push_back(a.xIdx - 1);
+            if (f->kind == MRB_ARBITRARY) {
+                if (vphi) vphi->push_back((int32_t)(s.phi_idx - 1));
+                if (va) va->push_back(s.alpha);
+            } else if (va) {
+                va->push_back(a.acc);                                   // Float64 phiIdx the taps are evaluated at
+            }
+            ++count;
+            arb_update(a, f->delta, f->Nphi);
+            if (f->kind == MRB_ARBITRARY) {
+                s.phi_idx = (int64_t)std::floor(a.acc);                 // :671-672
+                s.alpha = a.acc - (double)s.phi_idx;
+            }
+        }
+        s.phi_accumulator = a.acc;
+        s.x_idx = a.xIdx;
+        s.input_deficit = a.xIdx - n_in;                                // :734,:828
+    }
+    if (end) *end = s;
+    return count;
+}
+
+static int64_t count_outputs(const mrb_filter *f, int64_t n_in, mrb_state *end) {
+    if (is_table_kind(f)) return replay_table(f, n_in, end, nullptr, nullptr, nullptr);
+    int64_t p = f->phiIdx - 1, dd = f->deficit;
+    const int64_t N = IntSeq::count(f->L, f->M, p, dd, n_in);
+    IntSeq::advance(f->L, f->M, p, dd, n_in);
+    if (end) { *end = mrb_state{p + 1, dd, f->xIdx, f->acc, f->alpha}; }
+    return N;
+}
+
+extern "C" int32_t mrb_output_count(const mrb_filter *f, int64_t n_in, int64_t *n_out) {
+    if (!f || !n_out || n_in < 0) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    *n_out = count_outputs(f, n_in, nullptr);
+    return MRB_OK;
+}
+
+static void commit_state(mrb_filter *f, const mrb_state &s) {
+    f->phiIdx = s.phi_idx; f->deficit = s.input_deficit; f->xIdx = s.x_idx; f->acc = s.phi_accumulator; f->alpha = s.alpha;
+}
+
+extern "C" int32_t mrb_advance(mrb_filter *f, int64_t n_in, int64_t *n_out) {
+    if (!f || n_in < 0) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    mrb_state e;
+    const int64_t N = count_outputs(f, n_in, &e);
+    commit_state(f, e);
+    if (n_out) *n_out = N;
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_inputlength(int64_t n_out, int64_t L, int64_t M, int64_t phi, int64_t *n_in) {
+    if (!n_in || L < 1 || M < 1) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    *n_in = (int64_t)std::ceil((double)(n_out * M + phi - 1) / (double)L);                // :396-401
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_nextphase(int64_t cur, int64_t L, int64_t M, int64_t *next) {
+    if (!next || L < 1 || M < 1) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    const int64_t nx = cur + M % L;                                                       // :436-438
+    *next = nx > L ? nx - L : nx;
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_taps2pfb(const void *h, int64_t h_len, int32_t dtype, int64_t n_phi, void *pfb) {
+    if (!h || !pfb || h_len < 1 || n_phi < 1 || (dtype != MRB_F32 && dtype != MRB_F64))
+        return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    const int64_t T = ceil_div(h_len, n_phi);
+    int64_t hIdx = 0;
+    for (int64_t row = T - 1; row >= 0; --row)
+        for (int64_t col = 0; col < n_phi; ++col, ++hIdx) {
+            if (dtype == MRB_F32) static_cast<float *>(pfb)[col * T + row] = hIdx < h_len ? static_cast<const float *>(h)[hIdx] : 0.f;
+            else static_cast<double *>(pfb)[col * T + row] = hIdx < h_len ? static_cast<const double *>(h)[hIdx] : 0.0;
+        }
+    return MRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t mrb_reset(mrb_filter *f) {
+    if (!f) return fail(MRB_ERR_BAD_ARGUMENT, "null handle");
+    init_state(f);
+    if (f->device >= 0) {
+        CU(cudaSetDevice(f->device));
+        const size_t hb = (size_t)(f->H * f->nch) * dsize(f->tx);
+        CU(cudaDeviceSynchronize());
+        if (hb) CU(cudaMemset(f->d_hist[f->cur], 0, hb));
+        CU(cudaDeviceSynchronize());
+    }
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_setphase(mrb_filter *f, double phi) {
+    if (!f) return fail(MRB_ERR_BAD_ARGUMENT, "null handle");
+    if (!(phi >= 0.0 && phi <= 1.0)) return fail(MRB_ERR_BAD_ARGUMENT, "phase must be >= 0 and <= 1");   // :211,217,225
+    switch (f->kind) {
+    case MRB_RATIONAL:
+        f->phiIdx = std::min<int64_t>((int64_t)std::floor(phi * (double)f->Nphi) + 1, f->Nphi);
+        return MRB_OK;
+    case MRB_ARBITRARY: {
+        f->acc = 1.0 + phi * (double)f->Nphi;
+        f->phiIdx = std::min<int64_t>((int64_t)std::floor(f->acc), f->Nphi);
+        f->alpha = f->acc - (double)f->phiIdx;
+        return MRB_OK;
+    }
+    case MRB_FARROW:
+        f->acc = phi * (double)(f->Nphi - 1) + 1.0;                      // :226
+        return MRB_OK;
+    default: return fail(MRB_ERR_UNSUPPORTED, "setphase is not supported for this kernel (it carries no phase)");
+    }
+}
+
+extern "C" int32_t mrb_get_state(const mrb_filter *f, mrb_state *s) {
+    if (!f || !s) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    *s = mrb_state{f->phiIdx, f->deficit, f->xIdx, f->acc, f->alpha};
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_set_state(mrb_filter *f, const mrb_state *s) {
+    if (!f || !s) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    const int64_t maxphi = is_table_kind(f) ? f->Nphi : f->L;
+    if (s->phi_idx < 1 || s->phi_idx > maxphi || s->input_deficit < 1)
+        return fail(MRB_ERR_BAD_ARGUMENT, "state out of range");
+    if (is_table_kind(f) && !(s->phi_accumulator >= 1.0 && s->phi_accumulator < (double)(f->Nphi + 1)))
+        return fail(MRB_ERR_BAD_ARGUMENT, "phase accumulator out of range");
+    commit_state(f, *s);
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_get_history(mrb_filter *f, void *dst) {
+    if (!f || !dst) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    if (f->device < 0) return fail(MRB_ERR_NO_DEVICE, "host-only handle holds no history");
+    CU(cudaSetDevice(f->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(dst, f->d_hist[f->cur], (size_t)(f->H * f->nch) * dsize(f->tx), cudaMemcpyDeviceToHost));
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_set_history(mrb_filter *f, const void *src) {
+    if (!f || !src) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    if (f->device < 0) return fail(MRB_ERR_NO_DEVICE, "host-only handle holds no history");
+    CU(cudaSetDevice(f->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(f->d_hist[f->cur], src, (size_t)(f->H * f->nch) * dsize(f->tx), cudaMemcpyHostToDevice));
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_tapsforphase(const mrb_filter *f, double phase, void *taps) {
+    if (!f || !taps) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    if (!is_table_kind(f)) return fail(MRB_ERR_UNSUPPORTED, "tapsforphase is defined for arbitrary and farrow kernels");
+    if (!(phase >= 0.0 && phase <= (double)(f->Nphi + 1)))
+        return fail(MRB_ERR_BAD_ARGUMENT, "phase must be >= 0 and <= Nphi+1");            // :678,:765
+    for (int64_t i = 0; i < f->T; ++i) {
+        double v;
+        if (f->kind == MRB_ARBITRARY) {                                                   // :681-686
+            double ip;
+            const double a = std::modf(phase, &ip);
+            const int64_t phiIdx = (int64_t)ip;
+            if (phiIdx < 1 || phiIdx > f->Nphi) return fail(MRB_ERR_BAD_ARGUMENT, "phase selects branch %lld outside 1..Nphi", (long long)phiIdx);
+            v = f->bank[(phiIdx - 1) * f->T + i] + a * f->dbank[(phiIdx - 1) * f->T + i];
+        } else {                                                                          // :768-770
+            const double *c = &f->pnfb[i * (f->polyorder + 1)];
+            v = c[f->polyorder];
+            for (int p = f->polyorder - 1; p >= 0; --p) v = v * phase + c[p];
+        }
+        if (f->th == MRB_F32) static_cast<float *>(taps)[i] = (float)v;
+        else static_cast<double *>(taps)[i] = v;
+    }
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_get_pfb(const mrb_filter *f, int32_t which, void *dst) {
+    if (!f || !dst) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    const std::vector<double> &b = which == 0 ? f->bank : f->dbank;
+    if (which < 0 || which > 1 || b.empty()) return fail(MRB_ERR_BAD_ARGUMENT, "no such bank");
+    for (size_t i = 0; i < b.size(); ++i) {   // phase-major [phi][T] == Julia column-major T x Nphi
+        if (f->th == MRB_F32) static_cast<float *>(dst)[i] = (float)b[i];
+        else static_cast<double *>(dst)[i] = b[i];
+    }
+    return MRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// filt
+// ------------------------------------------------------------------------------------------
+template <typename RX, typename R, int NC>
+static void launch_generic(const GenParams &P, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(P.nout, 256), (unsigned)std::min<int64_t>(P.nch, 32768));
+    k_generic<RX, R, NC><<<grid, 256, 0, st>>>(P);
+}
+
+static void dispatch_generic(const mrb_filter *f, const GenParams &P, cudaStream_t st) {
+    const int key = f->tx * 4 + f->ty;
+    switch (key) {
+    case MRB_F32 * 4 + MRB_F32: launch_generic<float, float, 1>(P, st); break;
+    case MRB_C64 * 4 + MRB_C64: launch_generic<float, float, 2>(P, st); break;
+    case MRB_F32 * 4 + MRB_F64: launch_generic<float, double, 1>(P, st); break;
+    case MRB_C64 * 4 + MRB_C128: launch_generic<float, double, 2>(P, st); break;
+    case MRB_F64 * 4 + MRB_F64: launch_generic<double, double, 1>(P, st); break;
+    case MRB_C128 * 4 + MRB_C128: launch_generic<double, double, 2>(P, st); break;
+    }
+}
+
+static void launch_history(const mrb_filter *f, const void *x, int64_t ldx, int64_t n_in, const void *hold, void *hnew,
+                           int64_t nch, cudaStream_t st) {
+    if (f->H == 0) return;
+    const unsigned g = (unsigned)ceil_div(f->H * nch, 256);
+    switch (f->tx) {
+    case MRB_F32: k_history<float, 1><<<g, 256, 0, st>>>((const float *)x, ldx, n_in, (const float *)hold, (float *)hnew, f->H, nch); break;
+    case MRB_F64: k_history<double, 1><<<g, 256, 0, st>>>((const double *)x, ldx, n_in, (const double *)hold, (double *)hnew, f->H, nch); break;
+    case MRB_C64: k_history<float, 2><<<g, 256, 0, st>>>((const float *)x, ldx, n_in, (const float *)hold, (float *)hnew, f->H, nch); break;
+    case MRB_C128: k_history<double, 2><<<g, 256, 0, st>>>((const double *)x, ldx, n_in, (const double *)hold, (double *)hnew, f->H, nch); break;
+    }
+}
+
+static int32_t ensure_sched(mrb_filter *f) {
+    if (f->sched_cap) return MRB_OK;
+    for (auto &s : f->slot) {
+        CU(cudaMallocHost(&s.h_n, kSchedChunk * sizeof(int64_t)));
+        CU(cudaMallocHost(&s.h_phi, kSchedChunk * sizeof(int32_t)));
+        CU(cudaMallocHost(&s.h_a, kSchedChunk * sizeof(double)));
+        CU(cudaMalloc(&s.d_n, kSchedChunk * sizeof(int64_t)));
+        CU(cudaMalloc(&s.d_phi, kSchedChunk * sizeof(int32_t)));
+        CU(cudaMalloc(&s.d_a, kSchedChunk * sizeof(double)));
+        CU(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    }
+    if (f->kind == MRB_FARROW)
+        CU(cudaMalloc(&f->d_taptab, (size_t)kSchedChunk * f->T * (is_double(f->ty) ? 8 : 4)));
+    f->sched_cap = kSchedChunk;
+    return MRB_OK;
+}
+
+// Filter channels [c0, c0+nc) of one chunk from the CURRENT handle state (not committed here).
+// x / y point at channel c0.  N = exact output count for this chunk.
+static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n_in, void *y, int64_t ldy, int64_t N,
+                            int64_t c0, int64_t nc, cudaStream_t st) {
+    const size_t es = dsize(f->tx);
+    const char *hold = static_cast<const char *>(f->d_hist[f->cur]) + (size_t)(c0 * f->H) * es;
+    char *hnew = static_cast<char *>(f->d_hist[f->cur ^ 1]) + (size_t)(c0 * f->H) * es;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (f->timing && N > 0) {
+        CU(cudaEventCreate(&t0)); CU(cudaEventCreate(&t1));
+        CU(cudaEventRecord(t0, st));
+    }
+    if (N > 0) {
+        GenParams P{};
+        P.x = x; P.ldx = ldx; P.n_in = n_in; P.hist = hold; P.H = f->H; P.y = y; P.ldy = ldy;
+        P.bank = f->d_bank; P.dbank = f->d_dbank; P.T = f->T; P.nch = nc;
+        if (!is_table_kind(f)) {
+            P.mode = SEQ_INTEGER; P.L = f->L; P.M = f->M; P.p0 = f->phiIdx - 1; P.d0m1 = f->deficit - 1;
+            P.k_base = 0; P.nout = N;
+            bool done = false;
+            if (f->policy == 0) {
+                int32_t rc = tiled_try_launch(f->tiled, P, st, &f->last_kernel, &f->launches);
+                if (rc < 0) return fail(MRB_ERR_CUDA, "tiled launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                done = rc > 0;
+            }
+            if (!done) {
+                dispatch_generic(f, P, st);
+                f->last_kernel = "generic";
+                ++f->launches;
+            }
+        } else {
+            int32_t rc = ensure_sched(f);
+            if (rc) return rc;
+            // exact replay on the host (data independent), uploaded in bounded sub-chunks
+            std::vector<int64_t> vn; std::vector<int32_t> vphi; std::vector<double> va;
+            vn.reserve(N); va.reserve(N);
+            replay_table(f, n_in, nullptr, &vn, f->kind == MRB_ARBITRARY ? &vphi : nullptr, &va);
+            int si = 0;
+            for (int64_t k0 = 0; k0 < N; k0 += kSchedChunk, si ^= 1) {
+                const int64_t cnt = std::min(kSchedChunk, N - k0);
+                SchedSlot &s = f->slot[si];
+                if (s.pending) { CU(cudaEventSynchronize(s.ev)); s.pending = false; }
+                memcpy(s.h_n, vn.data() + k0, cnt * sizeof(int64_t));
+                memcpy(s.h_a, va.data() + k0, cnt * sizeof(double));
+                CU(cudaMemcpyAsync(s.d_n, s.h_n, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(s.d_a, s.h_a, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+                if (f->kind == MRB_ARBITRARY) {
+                    memcpy(s.h_phi, vphi.data() + k0, cnt * sizeof(int32_t));
+                    CU(cudaMemcpyAsync(s.d_phi, s.h_phi, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                }
+                CU(cudaEventRecord(s.ev, st));
+                s.pending = true;
+                P.sn = s.d_n; P.k_base = k0; P.nout = cnt;
+                if (f->kind == MRB_ARBITRARY) {
+                    P.mode = SEQ_ARBITRARY; P.sphi = s.d_phi; P.salpha = s.d_a;
+                } else {
+                    P.mode = SEQ_FARROW; P.taptab = f->d_taptab;
+                    const unsigned g = (unsigned)ceil_div(cnt * f->T, 256);
+                    if (is_double(f->ty))
+                        k_farrow_taps<double><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, cnt, (double *)f->d_taptab, f->th == MRB_F32);
+                    else
+                        k_farrow_taps<float><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, cnt, (float *)f->d_taptab, f->th == MRB_F32);
+                    ++f->launches;
+                }
+                dispatch_generic(f, P, st);
+                ++f->launches;
+            }
+            f->last_kernel = "generic";
+        }
+    }
+    if (t0) { CU(cudaEventRecord(t1, st)); f->tev.emplace_back(t0, t1); }
+    if (n_in > 0 && f->H > 0) {
+        launch_history(f, x, ldx, n_in, hold, hnew, nc, st);
+        ++f->launches;
+    }
+    CU(cudaGetLastError());
+    return MRB_OK;
+}
+
+static int32_t check_filt_args(mrb_filter *f, const void *x, int64_t ldx, int64_t n_in, void *y, int64_t ldy,
+                               int64_t cap, int64_t *N, mrb_state *end) {
+    if (!f) return fail(MRB_ERR_BAD_ARGUMENT, "null handle");
+    if (f->device < 0) return fail(MRB_ERR_NO_DEVICE, "host-only handle: no CUDA device bound, and there is no CPU fallback");
+    if (n_in < 0 || (n_in > 0 && !x) || ldx < n_in) return fail(MRB_ERR_BAD_ARGUMENT, "bad x / ld_x / n_in");
+    *N = count_outputs(f, n_in, end);
+    if (*N > cap) {
+        const char *msg = f->kind == MRB_STANDARD ? "buffer length must be >= x length"                    // :460
+                          : f->kind == MRB_INTERPOLATOR ? "length( buffer ) must be >= interpolation * length(x)"  // :503
+                                                        : "buffer is too small";                                   // :550
+        return fail(MRB_ERR_BUFFER_TOO_SMALL, "%s", msg);
+    }
+    if (*N > 0 && (!y || ldy < *N)) return fail(MRB_ERR_BAD_ARGUMENT, "bad y / ld_y");
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_filt(mrb_filter *f, const void *x, int64_t ldx, int64_t n_in, void *y, int64_t ldy,
+                            int64_t cap, int64_t *n_out, void *stream) {
+    int64_t N;
+    mrb_state end;
+    int32_t rc = check_filt_args(f, x, ldx, n_in, y, ldy, cap, &N, &end);
+    if (rc) return rc;
+    CU(cudaSetDevice(f->device));
+    rc = run_channels(f, x, ldx, n_in, y, ldy, N, 0, f->nch, (cudaStream_t)stream);
+    if (rc) return rc;
+    commit_state(f, end);
+    if (n_in > 0 && f->H > 0) f->cur ^= 1;
+    if (n_out) *n_out = N;
+    return MRB_OK;
+}
+
+static int32_t grow(void **p, size_t *have, size_t want) {
+    if (*have >= want) return MRB_OK;
+    cudaFree(*p);
+    *p = nullptr; *have = 0;
+    CU(cudaMalloc(p, want));
+    *have = want;
+    return MRB_OK;
+}
+
+// Host-buffer form: channel blocks are pipelined H2D -> kernels -> D2H on two streams so the copies of
+// one block overlap the compute of the other (PCIe is full duplex).
+extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int64_t n_in, void *y, int64_t ldy,
+                                 int64_t cap, int64_t *n_out) {
+    int64_t N;
+    mrb_state end;
+    int32_t rc = check_filt_args(f, x, ldx, n_in, y, ldy, cap, &N, &end);
+    if (rc) return rc;
+    CU(cudaSetDevice(f->device));
+    const size_t es = dsize(f->tx), eo = dsize(f->ty);
+    // channel block: ~64 MiB of input per block, at least 1 channel
+    int64_t cb = std::max<int64_t>(1, (int64_t)((64u << 20) / std::max<size_t>(1, (size_t)n_in * es)));
+    cb = std::min(cb, f->nch);
+    const size_t xb = (size_t)cb * std::max<int64_t>(n_in, 1) * es, yb = (size_t)cb * std::max<int64_t>(N, 1) * eo;
+    rc = grow(&f->d_xs, &f->xs_bytes, 2 * xb); if (rc) return rc;
+    rc = grow(&f->d_ys, &f->ys_bytes, 2 * yb); if (rc) return rc;
+    static thread_local cudaStream_t s2 = nullptr;
+    if (!s2) CU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    cudaStream_t sts[2] = {f->own_stream, s2};
+    int b = 0;
+    for (int64_t c0 = 0; c0 < f->nch; c0 += cb, b ^= 1) {
+        const int64_t nc = std::min(cb, f->nch - c0);
+        char *dx = static_cast<char *>(f->d_xs) + b * xb, *dy = static_cast<char *>(f->d_ys) + b * yb;
+        cudaStream_t st = sts[b];
+        if (n_in > 0)
+            CU(cudaMemcpy2DAsync(dx, (size_t)n_in * es, static_cast<const char *>(x) + (size_t)(c0 * ldx) * es,
+                                 (size_t)ldx * es, (size_t)n_in * es, (size_t)nc, cudaMemcpyHostToDevice, st));
+        rc = run_channels(f, dx, n_in, n_in, dy, std::max<int64_t>(N, 1), N, c0, nc, st);
+        if (rc) return rc;
+        if (N > 0)
+            CU(cudaMemcpy2DAsync(static_cast<char *>(y) + (size_t)(c0 * ldy) * eo, (size_t)ldy * eo, dy, (size_t)N * eo,
+                                 (size_t)N * eo, (size_t)nc, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(sts[0]));
+    CU(cudaStreamSynchronize(sts[1]));
+    commit_state(f, end);
+    if (n_in > 0 && f->H > 0) f->cur ^= 1;
+    if (n_out) *n_out = N;
+    return MRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// segment split
+// ------------------------------------------------------------------------------------------
+template <typename RX, int NC>
+__global__ void k_load_halo(const RX *__restrict__ halo, int64_t ld, RX *__restrict__ hist, int64_t H, int64_t nch) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= H * nch) return;
+    const int64_t c = idx / H, i = idx - c * H;
+    RX s[NC];
+    ld_sample<RX, NC>(halo + c * ld * NC, i, s);
+    st_sample<RX, NC>(hist + c * H * NC, i, s);
+}
+
+extern "C" int32_t mrb_seek(mrb_filter *f, int64_t n0, const void *halo, int64_t ld_halo, int64_t *k0, void *stream) {
+    if (!f || n0 < 0) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    if (is_table_kind(f)) return fail(MRB_ERR_UNSUPPORTED, "seek needs the integer schedule (arbitrary-rate start states require a replay)");
+    // state after consuming n0 samples from the constructor state (p=0, d=1): SURVEY 8e
+    const int64_t kk = ceil_div(n0 * f->L, f->M);
+    f->phiIdx = (kk * f->M) % f->L + 1;
+    f->deficit = (kk * f->M) / f->L - n0 + 1;
+    if (k0) *k0 = kk;
+    if (f->device >= 0 && f->H > 0) {
+        CU(cudaSetDevice(f->device));
+        cudaStream_t st = (cudaStream_t)stream;
+        void *dst = f->d_hist[f->cur];
+        if (!halo) {
+            CU(cudaMemsetAsync(dst, 0, (size_t)(f->H * f->nch) * dsize(f->tx), st));
+        } else {
+            if (ld_halo < f->H) return fail(MRB_ERR_BAD_ARGUMENT, "ld_halo < history_len");
+            const unsigned g = (unsigned)ceil_div(f->H * f->nch, 256);
+            switch (f->tx) {
+            case MRB_F32: k_load_halo<float, 1><<<g, 256, 0, st>>>((const float *)halo, ld_halo, (float *)dst, f->H, f->nch); break;
+            case MRB_F64: k_load_halo<double, 1><<<g, 256, 0, st>>>((const double *)halo, ld_halo, (double *)dst, f->H, f->nch); break;
+            case MRB_C64: k_load_halo<float, 2><<<g, 256, 0, st>>>((const float *)halo, ld_halo, (float *)dst, f->H, f->nch); break;
+            case MRB_C128: k_load_halo<double, 2><<<g, 256, 0, st>>>((const double *)halo, ld_halo, (double *)dst, f->H, f->nch); break;
+            }
+            ++f->launches;
+            CU(cudaGetLastError());
+        }
+    }
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_launch_count(const mrb_filter *f, int64_t *n) {
+    if (!f || !n) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    *n = f->launches;
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_set_kernel_policy(mrb_filter *f, int32_t policy) {
+    if (!f || policy < 0 || policy > 1) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    f->policy = policy;
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_set_timing(mrb_filter *f, int32_t on) {
+    if (!f) return fail(MRB_ERR_BAD_ARGUMENT, "null handle");
+    f->timing = on != 0;
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_get_timing(mrb_filter *f, double *mean_ms, int64_t *n_calls) {
+    if (!f || !mean_ms) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    double sum = 0.0;
+    for (auto &p : f->tev) {
+        CU(cudaEventSynchronize(p.second));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, p.first, p.second));
+        sum += ms;
+        cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+    }
+    *mean_ms = f->tev.empty() ? 0.0 : sum / (double)f->tev.size();
+    if (n_calls) *n_calls = (int64_t)f->tev.size();
+    f->tev.clear();
+    return MRB_OK;
+}
+
+extern "C" const char *mrb_last_kernel(const mrb_filter *f) { return f ? f->last_kernel : "none"; }
+extern "C" const char *mrb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *mrb_version(void) { return "libmrb 0.1.0 (sm_100a)"; }

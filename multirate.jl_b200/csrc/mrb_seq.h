@@ -1,0 +1,59 @@
+// mrb_seq.h -- host-side sequencing: output counts, phase/deficit carry and the exact
+// replay of the arbitrary-rate phase accumulators.  Pure C++ (no CUDA), shared by the
+// API layer; everything here is data independent and channel independent.
+//
+// Reference: src/Filters.jl:352-385 (outputlength), :433-439 (nextphase), :536-575
+// (rational loop), :598-631 (decimator loop), :663-673 / :780-786 (update).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+namespace mrb {
+
+static inline int64_t ceil_div(int64_t a, int64_t b) {   // b > 0
+    return a >= 0 ? (a + b - 1) / b : -((-a) / b);
+}
+static inline int64_t floor_div(int64_t a, int64_t b) {  // b > 0
+    return a >= 0 ? a / b : -((-a + b - 1) / b);
+}
+
+// Integer schedule shared by standard (L=M=1), interpolator (M=1), decimator (L=1) and
+// rational.  State: p = phiIdx-1 (0-based phase), d = inputDeficit (1-based).
+// Output k (0-based) of a chunk reads the window ending at 1-based input index
+//   n_k = d + floor((p + k*M)/L)          with branch  phi_k = (p + k*M) mod L.
+// This is the closed form of the loop at src/Filters.jl:558-569 (:567 advances inputIdx by
+// floor((phiIdx+M-1)/L), :568 is nextphase); tests/test_host_logic.py checks it against the
+// literal loop of the oracle.
+struct IntSeq {
+    int64_t L, M;
+    // number of outputs for xLen inputs from state (p, d); src/Filters.jl:352-357,371-373
+    static int64_t count(int64_t L, int64_t M, int64_t p, int64_t d, int64_t xLen) {
+        if (xLen < d) return 0;
+        return ceil_div((xLen - d + 1) * L - p, M);
+    }
+    // state after the chunk
+    static void advance(int64_t L, int64_t M, int64_t &p, int64_t &d, int64_t xLen) {
+        if (xLen < d) { d -= xLen; return; }                     // :543-547
+        const int64_t N = count(L, M, p, d, xLen);
+        const int64_t t = p + N * M;
+        d = d + t / L - xLen;                                     // :571
+        p = t % L;
+    }
+};
+
+// FIRArbitrary.update / FIRFarrow.update, src/Filters.jl:663-673, 780-786.  Sequentially
+// rounded Float64 recurrence: replayed literally (compile with -ffp-contract=off).
+struct ArbState {
+    double acc;     // phiAccumulator (arbitrary) / Float64 phiIdx (farrow), in [1, Nphi+1)
+    int64_t xIdx;   // 1-based
+};
+static inline void arb_update(ArbState &s, double delta, int64_t Nphi) {
+    s.acc += delta;
+    if (s.acc > (double)Nphi) {
+        s.xIdx += (int64_t)std::floor((s.acc - 1.0) / (double)Nphi);
+        s.acc = std::fmod(s.acc - 1.0, (double)Nphi) + 1.0;
+    }
+}
+
+}  // namespace mrb

@@ -1,0 +1,281 @@
+"""Parity of the CUDA path (through the C-ABI, libmrb.so) against the oracle.  Needs a B200.
+
+Bar (north_star): output COUNT, PHASE sequencing and carried STATE bit-exact for every kernel type and
+chunking, including the empty-output cases; VALUES within 1e-5 (Float32 / Complex64) and 1e-12
+(Float64 / Complex128) of the oracle, error normalised by max|y|."""
+import ctypes as C
+import json
+import os
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import multirate_b200 as mr
+import multirate_oracle as mo
+from conftest import nerr, rand_samples, tol_for
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+KAT = json.load(open(os.path.join(GOLD, "kat.json")))
+F = mr._ffi
+
+
+def states_equal(f, o):
+    s, so = f._get_state(), o.state()
+    ok = s.phi_idx == so.get("phiIdx", s.phi_idx) and s.input_deficit == so.get("inputDeficit", 1)
+    if "acc" in so:
+        ok = ok and s.phi_accumulator == so["acc"]
+    if "alpha" in so:
+        ok = ok and s.alpha == so["alpha"]
+    return ok
+
+
+def test_extension_is_loaded_and_device_is_b200():
+    import torch
+    assert torch.cuda.is_available()
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    assert os.path.exists(F.LIB)
+    maps = open("/proc/self/maps").read()
+    F.lib()
+    assert "libmrb.so" in open("/proc/self/maps").read() or "libmrb.so" in maps
+
+
+def test_readme_3_17_kat_on_gpu():
+    k = KAT["readme_3_17"]
+    h, x = np.array(k["h"], dtype=np.float64), np.array(k["x"], dtype=np.float64)
+    f = mr.FIRFilter(h, Fraction(*k["ratio"]))
+    pos, ys = 0, []
+    for n, want in zip(k["chunks"], k["y"]):
+        y = mr.filt(f, x[pos:pos + n]); pos += n
+        assert np.array_equal(y, np.array(want)), (y, want)
+        ys.append(y)
+    assert np.sum(np.concatenate(ys) - mr.filt(h, x, Fraction(*k["ratio"]))) == 0.0
+    assert f.kernel.phiIdx == 2 and f.kernel.inputDeficit >= 1
+
+
+def test_farrow_notebook_count_on_gpu():
+    k = KAT["farrow_notebook_count"]
+    N = k["Nphi"]
+    h = mo.firdes(k["tapsPerphi"] * N, min(0.45 / N, k["rate"] / N)) * N
+    t = np.arange(k["n_in"])
+    x = np.cos(2 * np.pi * 0.15 * t) + 0.5 * np.sin(2 * np.pi * 0.3 * t * np.pi)
+    assert len(mr.filt(h, x, k["rate"], N, k["polyorder"])) == k["n_out"]
+
+
+def test_golden_oracle_vectors():
+    """Frozen vectors (tests/golden/oracle_vectors.npz): all 7 cases x 2 tap dtypes x 4 sample dtypes, 3 chunks
+    (1 sample / 39 / 291), 2 channels, values + end state."""
+    g = np.load(os.path.join(GOLD, "oracle_vectors.npz"))
+    names = sorted({k.rsplit(".", 1)[0] for k in g.files})
+    ratios = {"standard": Fraction(1, 1), "decimator": Fraction(1, 8), "interpolator": Fraction(4, 1),
+              "rational": Fraction(147, 160), "rational_3_17": Fraction(3, 17)}
+    for key in names:
+        name, th, tx = key.split(".")
+        h, x = g[key + ".h"], g[key + ".x"]
+        if name == "arbitrary":
+            f = mr.FIRFilter(h, 0.918734, 32)
+        elif name == "farrow":
+            f = mr.FIRFilter(h, 0.918734, 32, 4)
+        else:
+            f = mr.FIRFilter(h, ratios[name])
+        for i, (a, b) in enumerate(((0, 1), (1, 40), (40, 331))):
+            y = f.filt(x[:, a:b])
+            want = g[key + ".y%d" % i]
+            assert y.dtype == want.dtype and y.shape == want.shape, key
+            assert nerr(y, want) <= tol_for(y.dtype), (key, i, nerr(y, want))
+        s = f._get_state()
+        if name.startswith("rational") or name == "decimator":
+            assert [s.phi_idx, s.input_deficit] == g[key + ".state"].tolist(), key
+        if name in ("arbitrary", "farrow"):
+            assert s.input_deficit == g[key + ".state"][1] and s.phi_accumulator == g[key + ".fstate"][0], key
+        if name == "arbitrary":
+            assert s.alpha == g[key + ".fstate"][1]
+
+
+@pytest.mark.parametrize("th", [np.float32, np.float64])
+@pytest.mark.parametrize("tx", [np.float32, np.float64, np.complex64, np.complex128])
+def test_four_way_equivalence_gpu(th, tx, rng):
+    """The reference's own test matrix (test/runtests.jl:389-421), seeded: naive definition == oracle ==
+    GPU one-shot == GPU 2-chunk == GPU sample-at-a-time (exercises empty returns and deficit carry)."""
+    Ls = [1] + sorted(set(rng.integers(2, 33, 3).tolist()))
+    Ms = [1] + sorted(set(rng.integers(2, 33, 3).tolist()))
+    for L in Ls:
+        for M in Ms:
+            ratio = Fraction(L, M)
+            h = rng.random(int(rng.integers(16, 129))).astype(th)
+            xLen = int(rng.integers(200, 301)); xLen -= xLen % M
+            x = rand_samples(rng, xLen, tx)
+            ty = np.result_type(th, tx)
+            tol = tol_for(ty)
+            naive = mo.naivefilt(h, x, ratio)
+            want = mo.filt(h, x, ratio)
+            one = mr.filt(h, x, ratio)
+            assert one.dtype == ty and one.shape == want.shape
+            assert nerr(one, want) <= tol, (L, M, nerr(one, want))
+            assert nerr(one, naive.astype(ty)) <= max(tol, 2e-6)
+            f, o = mr.FIRFilter(h, ratio), mo.FIRFilter(h, ratio)
+            piv = min(int(rng.integers(50, 151)), xLen // 4)
+            two = np.concatenate([f.filt(x[:piv]), f.filt(x[piv:])])
+            o.filt(x[:piv]); o.filt(x[piv:])
+            assert nerr(two, want) <= tol and states_equal(f, o)
+            f.reset(); o.reset()
+            parts = []
+            for i in range(piv):                                     # test/runtests.jl:81-83,150-152,311-313
+                yi, oi = f.filt(x[i:i + 1]), o.filt(x[i:i + 1])
+                assert len(yi) == len(oi)                            # empty returns included
+                parts.append(yi)
+            parts.append(f.filt(x[piv:])); o.filt(x[piv:])
+            assert nerr(np.concatenate(parts), want) <= tol and states_equal(f, o)
+
+
+@pytest.mark.parametrize("th,tx", [(np.float32, np.float32), (np.float32, np.complex64), (np.float64, np.float64),
+                                   (np.float64, np.complex128), (np.float64, np.float32), (np.float32, np.float64)])
+@pytest.mark.parametrize("polyorder", [None, 4])
+def test_arbitrary_and_farrow_gpu(th, tx, polyorder, rng):
+    """FIRArbitrary / FIRFarrow against the oracle: counts, accumulator, alpha and deficit bit-exact after every
+    chunk (1-sample chunks included), values within tolerance; multi-channel."""
+    N = 32
+    hLen, beta = mo.kaiserlength(0.05, samplerate=N)
+    hLen = -(-hLen // N) * N
+    h = (mo.firdes(hLen, 0.45, beta, samplerate=32) * N).astype(th)          # test/runtests.jl:336-341
+    x = rand_samples(rng, (3, 700), tx)
+    for rate in (0.918734, 1 / 2.123456789, 2.5):
+        f, o = mr.FIRFilter(h, rate, N, polyorder), mo.FIRFilter(h, rate, N, polyorder)
+        pos = 0
+        for n in [1, 1, 0, 3, 95, 1, 600 - 101]:
+            y, w = f.filt(x[:, pos:pos + n]), o.filt(x[:, pos:pos + n]); pos += n
+            assert y.shape == w.shape and y.dtype == w.dtype
+            assert nerr(y, w) <= tol_for(w.dtype), (rate, n, nerr(y, w))
+            assert states_equal(f, o)
+        one = mr.filt(h, x[0], rate, N, polyorder) if polyorder is not None else mr.filt(h, x[0], rate, N)
+        assert nerr(one, mo.filt(h, x[0], rate, N, polyorder)) <= tol_for(one.dtype)
+
+
+def test_errors_and_edge_cases(rng):
+    h = rng.random(33).astype(np.float32)
+    x = rand_samples(rng, 64, np.float32)
+    f = mr.FIRFilter(h, Fraction(3, 4))
+    with pytest.raises(mr.MrbError, match="buffer is too small") as e:        # src/Filters.jl:550
+        f.filt_(np.empty(3, np.float32), x)
+    assert e.value.code == F.MRB_ERR_BUFFER_TOO_SMALL
+    with pytest.raises(mr.MrbError, match="buffer length must be >= x length"):   # :460
+        mr.FIRFilter(h).filt_(np.empty(3, np.float32), x)
+    with pytest.raises(mr.MrbError, match="must be >= interpolation"):        # :503
+        mr.FIRFilter(h, Fraction(3, 1)).filt_(np.empty(3, np.float32), x)
+    # filt! return conventions (:472,516 buffer ; :574,630,741,835 count)
+    buf = np.empty(200, np.float32)
+    assert mr.filt_(buf, mr.FIRFilter(h), x) is buf
+    assert mr.filt_(buf, mr.FIRFilter(h, Fraction(1, 4)), x) == 16
+    assert mr.filt_(buf, f, x) == 48
+    # empty input, empty output
+    d = mr.FIRFilter(h, Fraction(1, 8))
+    assert len(d.filt(x[:0])) == 0 and d.kernel.inputDeficit == 1
+    assert len(d.filt(x[:1])) == 1 and d.kernel.inputDeficit == 8
+    for i in range(1, 8):
+        assert len(d.filt(x[i:i + 1])) == 0 and d.kernel.inputDeficit == 8 - i
+    assert len(d.filt(x[8:9])) == 1
+    # history carry when the chunk is shorter than the history (shiftin!, src/support.jl:69-76)
+    o = mo.FIRFilter(h, Fraction(1, 8))
+    for a, b in [(0, 1), (1, 9)]:
+        o.filt(x[a:b])
+    assert np.array_equal(d.history, o.history[0])
+    # one tap (historyLen == 0)
+    assert nerr(mr.filt(np.array([2.0]), np.arange(8.0)), 2.0 * np.arange(8.0)) == 0.0
+
+
+def test_multichannel_matches_per_channel(rng):
+    """Channels are independent and share one state machine: a (C, n) batch == C single-channel filters."""
+    h = mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32)
+    x = rand_samples(rng, (37, 3000), np.complex64)
+    f = mr.FIRFilter(h, Fraction(147, 160))
+    y = np.concatenate([f.filt(x[:, :1111]), f.filt(x[:, 1111:])], axis=1)
+    for c in (0, 1, 17, 36):
+        assert nerr(y[c], mo.filt(h, x[c], Fraction(147, 160))) <= 1e-5
+    assert y.shape == (37, mo.FIRFilter(h, Fraction(147, 160)).outputlength(3000))
+
+
+@pytest.mark.parametrize("case", ["rational", "decimator", "interpolator", "standard"])
+def test_device_path_torch_streaming(case, rng):
+    """Zero-copy device path (mrb_filt on torch's stream): state stays on the device between 64K-sample
+    chunks; compared with the host path and the oracle; generic and tiled kernels must agree."""
+    import torch
+    cfg = {"rational": (Fraction(147, 160), 24 * 147, np.complex64, 0.5 / 147),
+           "decimator": (Fraction(1, 8), 256, np.complex64, 0.5 / 8),
+           "interpolator": (Fraction(4, 1), 128, np.float32, 0.5 / 4),
+           "standard": (Fraction(1, 1), 128, np.float32, 0.25)}[case]
+    ratio, ntaps, tx, cutoff = cfg
+    h = mo.firdes(ntaps, cutoff, 7.8562).astype(np.float32)
+    nch, chunk = 70, 1 << 14
+    x = rand_samples(rng, (nch, 3 * chunk + 5), tx)
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, ratio)
+    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
+    g.set_kernel_policy(1)                                            # force the generic kernel
+    o = mo.FIRFilter(h, ratio)
+    edges = [0, chunk, chunk + 1, 2 * chunk + 3, 3 * chunk + 5]
+    for a, b in zip(edges[:-1], edges[1:]):
+        yd = f.filt(xd[:, a:b])
+        yg = g.filt(xd[:, a:b])
+        w = o.filt(x[:5, a:b])
+        torch.cuda.synchronize()
+        assert yd.is_cuda and tuple(yd.shape) == (nch, w.shape[1])
+        y = yd.cpu().numpy()
+        assert nerr(y[:5], w) <= 1e-5, (case, nerr(y[:5], w))
+        assert nerr(yg.cpu().numpy(), y) <= 2e-6
+        assert states_equal(f, o)
+    assert f.last_kernel != "none" and g.last_kernel == "generic"
+    assert f.launch_count > 0
+
+
+def test_full_size_properties_c5_shard(rng):
+    """BASELINE config 5 at full per-GPU chunk size, properties that need no oracle run over the whole
+    batch: (i) exact count; (ii) chunking invariance (64K one-shot == 4 x 16K streamed, same kernel family =>
+    bit-identical values); (iii) linearity in x; (iv) channel independence (a channel's output does not
+    depend on its neighbours); spot rows checked against the oracle."""
+    import torch
+    h = mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32)
+    nch, n = 1024, 1 << 16
+    gen = torch.Generator(device="cuda"); gen.manual_seed(0x4D520005)
+    x = torch.view_as_complex(torch.rand((nch, n, 2), generator=gen, device="cuda"))
+    ratio = Fraction(147, 160)
+    y1 = mr.FIRFilter(h, ratio).filt(x)
+    assert y1.shape[1] == 60212 == mo.FIRFilter(h, ratio).outputlength(n)
+    f = mr.FIRFilter(h, ratio)
+    y4 = torch.cat([f.filt(x[:, i * 16384:(i + 1) * 16384]) for i in range(4)], dim=1)
+    assert torch.equal(torch.view_as_real(y1), torch.view_as_real(y4))
+    y2 = mr.FIRFilter(h, ratio).filt(2 * x)
+    assert torch.equal(torch.view_as_real(y2), torch.view_as_real(2 * y1))
+    xs = x[100:164].clone()
+    ys = mr.FIRFilter(h, ratio).filt(xs)
+    assert (ys - y1[100:164]).abs().max().item() <= 1e-5 * y1.abs().max().item()
+    rows = [0, 511, 1023]
+    w = mo.filt(h, x[rows].cpu().numpy(), ratio)
+    assert nerr(y1[rows].cpu().numpy(), w) <= 1e-5
+
+
+def test_segment_split_matches_stream(rng):
+    """Long-stream split: S independent segments, each seeked to its closed-form start state with a
+    tap-length halo, reproduce the single-stream output exactly; no collective involved."""
+    import torch
+    h = mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32)
+    ratio = Fraction(147, 160)
+    n = 200_003
+    x = torch.from_numpy(rand_samples(rng, (1, n), np.complex64)).cuda()
+    whole = mr.FIRFilter(h, ratio).filt(x)
+    bounds = [0, 50_001, 99_999, 160_000, n]
+    parts = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        f = mr.FIRFilter(h, ratio, nchannels=1, sample_dtype=np.complex64)
+        H = f.historyLen
+        k0 = C.c_int64()
+        halo = None
+        if a > 0:
+            halo = x[:, a - H:a].contiguous()
+        F.check(F.lib().mrb_seek(f._handle, a, halo.data_ptr() if halo is not None else None, H, C.byref(k0),
+                                 torch.cuda.current_stream().cuda_stream))
+        assert k0.value == sum(p.shape[1] for p in parts)
+        parts.append(f.filt(x[:, a:b]))
+    got = torch.cat(parts, dim=1)
+    assert got.shape == whole.shape
+    assert torch.equal(torch.view_as_real(got), torch.view_as_real(whole))

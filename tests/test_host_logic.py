@@ -1,0 +1,154 @@
+"""Host logic of the library on a host-only handle (device = -1): counts, phase sequencing and carried
+state must be EXACT against the oracle for every kernel type and any chunking.  CPU only."""
+import ctypes as C
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import multirate_b200 as mr
+import multirate_oracle as mo
+
+F = mr._ffi
+
+
+def advance(f, n):
+    N = C.c_int64()
+    F.check(F.lib().mrb_advance(f._handle, n, C.byref(N)))
+    return N.value
+
+
+def state_tuple(f):
+    s = f._get_state()
+    return s.phi_idx, s.input_deficit, s.phi_accumulator, s.alpha
+
+
+@pytest.mark.parametrize("L,M", [(1, 1), (1, 2), (1, 8), (1, 31), (2, 1), (4, 1), (32, 1), (3, 17), (17, 3),
+                                 (147, 160), (160, 147), (7, 5), (31, 32), (32, 31)])
+def test_integer_sequencing_exact(L, M, rng):
+    h = rng.random(int(rng.integers(1, 200)))
+    f = mr.FIRFilter(h, Fraction(L, M), nchannels=1, sample_dtype=np.float64, device=-1)
+    o = mo.FIRFilter(h, Fraction(L, M))
+    assert type(f.kernel).__name__ == type(o.kernel).__name__
+    assert f.historyLen == o.historyLen
+    chunks = [0, 1, 1, 1, 2, 5, 18, 77, 0, 1, 300, 1, 1, 64, 1000]
+    for n in chunks:
+        assert f.outputlength(n) == o.outputlength(n) or n < o.state().get("inputDeficit", 1)
+        want = len(o.filt(rng.random(n)))
+        cnt = C.c_int64(); F.check(F.lib().mrb_output_count(f._handle, n, C.byref(cnt)))
+        assert cnt.value == want
+        assert advance(f, n) == want
+        so = o.state()
+        p, d, _, _ = state_tuple(f)
+        assert p == so.get("phiIdx", 1) and d == so.get("inputDeficit", 1)
+
+
+@pytest.mark.parametrize("polyorder", [None, 4])
+@pytest.mark.parametrize("rate", [0.918734, 1.0, 1 / 2.123456789, float(np.pi), 31.7])
+def test_table_sequencing_bit_exact(rate, polyorder, rng):
+    """FIRArbitrary / FIRFarrow: the Float64 accumulator, alpha and deficit after every chunk are
+    bit-for-bit the oracle's (src/Filters.jl:663-673, 780-786)."""
+    h = rng.random(320)
+    f = mr.FIRFilter(h, rate, 32, polyorder, nchannels=1, sample_dtype=np.float64, device=-1)
+    o = mo.FIRFilter(h, rate, 32, polyorder)
+    for n in [0, 1, 1, 1, 3, 40, 1, 777, 5000]:
+        want = len(o.filt(rng.random(n)))
+        assert advance(f, n) == want
+        so = o.state()
+        p, d, acc, alpha = state_tuple(f)
+        assert d == so["inputDeficit"] and acc == so["acc"]
+        if polyorder is None:
+            assert p == so["phiIdx"] and alpha == so["alpha"]
+        assert f.outputlength(50) == o.outputlength(50)
+
+
+def test_readme_struct_fields():
+    f = mr.FIRFilter(np.r_[np.ones(3), np.zeros(6)], Fraction(3, 17))
+    k = f.kernel
+    assert isinstance(k, mr.FIRRational)
+    assert np.array_equal(k.pfb, [[0, 0, 0], [0, 0, 0], [1, 1, 1]])
+    assert (k.ratio, k.Nphi, k.tapsPerphi, k.phiIdx, k.inputDeficit) == (Fraction(3, 17), 3, 3, 1, 1)
+    assert f.historyLen == 2 and np.array_equal(f.history, [0.0, 0.0])
+
+
+def test_kernel_selection_and_errors():
+    h = np.ones(12)
+    assert isinstance(mr.FIRFilter(h).kernel, mr.FIRStandard)
+    assert isinstance(mr.FIRFilter(h, Fraction(3, 3)).kernel, mr.FIRStandard)        # README.md:31-32 / SURVEY 9.6
+    assert isinstance(mr.FIRFilter(h, Fraction(1, 3)).kernel, mr.FIRDecimator)
+    assert isinstance(mr.FIRFilter(h, Fraction(3, 1)).kernel, mr.FIRInterpolator)
+    assert isinstance(mr.FIRFilter(h, Fraction(6, 8)).kernel, mr.FIRRational)
+    assert mr.FIRFilter(h, Fraction(6, 8)).kernel.ratio == Fraction(3, 4)
+    assert isinstance(mr.FIRFilter(h, 0.5).kernel, mr.FIRArbitrary)
+    assert mr.FIRFilter(h, 0.5).kernel.Nphi == 32
+    assert isinstance(mr.FIRFilter(h, 0.5, 4, 2).kernel, mr.FIRFarrow)
+    with pytest.raises(ValueError, match="rate must be greater than 0"):
+        mr.FIRFilter(h, -1.0)
+    d = F.Desc(); d.kind = F.KIND_AUTO; d.tap_dtype = F.F64; d.sample_dtype = F.F32; d.device = -1
+    hh = np.ones(4); d.h = hh.ctypes.data; d.h_len = 4; d.interpolation = 1; d.decimation = 1; d.rate = -2.0
+    d.n_phi = 32; d.poly_order = -1; d.n_channels = 1
+    out = C.c_void_p()
+    assert F.lib().mrb_create(C.byref(d), C.byref(out)) == F.MRB_ERR_BAD_ARGUMENT
+    assert b"rate must be greater than 0" in F.lib().mrb_last_error()
+
+
+def test_nextphase_taps2pfb_lengths(rng):
+    for L in range(1, 9):
+        for M in range(1, 9):
+            r = Fraction(L, M)
+            for p in range(1, r.numerator + 1):
+                assert mr.nextphase(p, r) == mo.nextphase(p, r)
+    for n, nphi in [(9, 4), (3528, 147), (5, 7), (2336, 32)]:
+        h = rng.random(n)
+        assert np.array_equal(mr.taps2pfb(h, nphi), mo.taps2pfb(h, nphi))
+        h32 = h.astype(np.float32)
+        assert np.array_equal(mr.taps2pfb(h32, nphi), mo.taps2pfb(h32, nphi))
+    for outlen, (L, M), phi in [(10, (3, 17), 2), (918750, (147, 160), 1), (7, (1, 8), 1)]:
+        assert mr.inputlength(outlen, Fraction(L, M), phi) == mo.inputlength_ratio(outlen, Fraction(L, M), phi)
+        assert mr.outputlength(outlen, Fraction(L, M), phi) == mo.outputlength_ratio(outlen, Fraction(L, M), phi)
+
+
+def test_tapsforphase_and_banks(rng):
+    h = rng.random(300).astype(np.float32)
+    fa, oa = mr.FIRFilter(h, 1.3), mo.FIRFilter(h, 1.3)
+    ff, of = mr.FIRFilter(h, 1.3, 32, 4), mo.FIRFilter(h, 1.3, 32, 4)
+    assert np.array_equal(fa.kernel.pfb, oa.kernel.pfb) and np.array_equal(fa.kernel.dpfb, oa.kernel.dpfb)
+    assert np.array_equal(ff.kernel.pnfb, of.kernel.pnfb)
+    for ph in [1.0, 1.5, 7.25, 32.0, 32.999]:
+        assert np.array_equal(mr.tapsforphase(fa.kernel, ph), mo.tapsforphase_arbitrary(oa.kernel, ph))
+        assert np.array_equal(mr.tapsforphase(ff.kernel, ph), mo.tapsforphase_farrow(of.kernel, ph))
+    assert np.array_equal(ff.kernel.currentTaps, of.kernel.currentTaps)
+    with pytest.raises(ValueError, match="phase must be"):
+        mr.tapsforphase(fa.kernel, 34.0)
+    with pytest.raises(ValueError, match="buffer is too small"):
+        mr.tapsforphase_(np.empty(2, np.float32), fa.kernel, 1.0)
+
+
+def test_setphase_and_deficit_poke():
+    h = np.ones(64)
+    f = mr.FIRFilter(h, float(np.pi), 32, 4)
+    f.kernel.inputDeficit += 3                       # examples/FIRFarrow.jl:29
+    assert f.kernel.inputDeficit == 4
+    assert f.setphase(0.5) == 0.5 * 31 + 1           # src/Filters.jl:226
+    a = mr.FIRFilter(h, 0.7)
+    phi, alpha = a.setphase(0.26)
+    assert (phi, alpha) == (9, 1 + 0.26 * 32 - 9) and a.kernel.phiAccumulator == 1 + 0.26 * 32
+    r = mr.FIRFilter(h, Fraction(3, 4))
+    assert r.setphase(0.5) == 2 and r.setphase(1.0) == 3 and r.setphase(0.0) == 1
+    with pytest.raises(AssertionError):
+        r.setphase(1.5)
+    with pytest.raises(mr.MrbError):
+        mr.FIRFilter(h, Fraction(3, 1)).setphase(0.5)
+
+
+@pytest.mark.parametrize("L,M", [(147, 160), (3, 17), (1, 8), (4, 1), (1, 1), (17, 3)])
+def test_seek_closed_form(L, M, rng):
+    """Segment start state: seek(n0) == the state after filtering n0 samples."""
+    h = rng.random(97)
+    for n0 in [0, 1, 2, 159, 160, 161, 1000, 4097, 2 ** 31 - 5]:
+        a = mr.FIRFilter(h, Fraction(L, M), nchannels=1, sample_dtype=np.float32, device=-1)
+        b = mr.FIRFilter(h, Fraction(L, M), nchannels=1, sample_dtype=np.float32, device=-1)
+        k0 = C.c_int64()
+        F.check(F.lib().mrb_seek(a._handle, n0, None, 0, C.byref(k0), None))
+        assert advance(b, n0) == k0.value
+        assert state_tuple(a)[:2] == state_tuple(b)[:2]
