@@ -520,15 +520,14 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
         if (!is_table_kind(f)) {
             P.mode = SEQ_INTEGER; P.L = f->L; P.M = f->M; P.p0 = f->phiIdx - 1; P.d0m1 = f->deficit - 1;
             P.k_base = 0; P.nout = N;
-            bool done = false;
+            int64_t k_begin = -1;
             if (f->policy == 0) {
-                int32_t rc = tiled_try_launch(f->tiled, P, st, &f->last_kernel, &f->launches);
-                if (rc < 0) return fail(MRB_ERR_CUDA, "tiled launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-                done = rc > 0;
+                k_begin = tiled_try_launch(f->tiled, P, st, &f->last_kernel, &f->launches);
+                if (k_begin == -2) return fail(MRB_ERR_CUDA, "tiled launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
-            if (!done) {
+            if (k_begin != 0) {            // generic kernel: everything, or the head the tiled kernel left out
+                if (k_begin > 0) P.nout = k_begin; else f->last_kernel = "generic";
                 dispatch_generic(f, P, st);
-                f->last_kernel = "generic";
                 ++f->launches;
             }
         } else {

@@ -1,13 +1,352 @@
-// mrb_tiled.cuh -- tiled fast paths (stub; replaced by the real kernels)
+// mrb_tiled.cuh -- the tiled fast path for integer-schedule kernels with unit input stride
+// (FIRStandard, and FIRRational with L <= M < 2L such as 147//160), complex64 or float32 samples.
+//
+// Mapping (B200, sm_100a), measured pipe rates in tools/ubench*.cu and DESIGN.md:
+//  * lane = channel.  A CTA is 2 warps = 64 channels; every thread walks the SAME outputs, so the whole
+//    phase / input-index bookkeeping (src/Filters.jl:567-568) is warp-uniform and lives in the uniform
+//    datapath (UIADD3 / UISETP), never in vector registers.
+//  * taps: the flipped phase-major bank (taps2pfb, src/Filters.jl:284-298) is a __grid_constant__ kernel
+//    parameter; with a uniform phase index ptxas emits LDCU.64 c[0x0][UR+imm] and feeds FFMA2 a
+//    uniform-register operand -- taps cost no shared-memory bandwidth and no vector registers.
+//  * samples: TMA (cp.async.bulk.tensor.2d, SWIZZLE_64B) streams [64 channels][8 samples] boxes of x into a
+//    shared-memory ring; each thread reads its channel's window with conflict-free LDS.128 into registers.
+//  * outputs are grouped into RUNS: maximal sets of <= RMAX consecutive outputs whose input index advances
+//    by exactly one per output (the phase does not wrap inside a run).  Inside a run the window register
+//    index of (output r, tap i) is the compile-time constant r+i, so the dot products (unsafedot,
+//    src/support.jl:5-14) are straight-line FFMA2 on registers: one complex x real FMA = one FFMA2.
+//  * results are staged in shared memory ([64 channels][8 outputs], SWIZZLE_64B) and written with TMA stores,
+//    so global writes are full 64-byte rows instead of 8-byte scatters.
+// Outputs whose window touches the history (the first ~T outputs of a chunk) and every configuration this
+// kernel does not cover are computed by k_generic (mrb_kernels.cuh) -- still on the GPU.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <vector>
+
 #include "mrb_kernels.cuh"
+#include "mrb_seq.h"
+
 namespace mrb {
-struct TiledPlan { int dummy = 0; };
-static inline int32_t tiled_prepare(TiledPlan &, int, int, int, int64_t, int64_t, int64_t, int64_t,
-                                    const std::vector<double> &, const std::vector<double> &, const cudaDeviceProp &) { return 0; }
-static inline int32_t tiled_try_launch(TiledPlan &, const GenParams &, cudaStream_t, const char **, int64_t *) { return 0; }
-static inline void tiled_release(TiledPlan &) {}
+
+constexpr int kTiledRows = 64;          // channels per CTA (2 warps)
+constexpr int kBoxSamples = 8;          // samples per TMA box row (64 B for complex64)
+constexpr int kBankFloats = 6144;       // tap bank capacity in kernel-parameter space (24 KiB)
+constexpr int kMaxTiles = 192;          // time tiles per launch (their start states ride in parameter space)
+constexpr int kMaxPhases = 1024;
+constexpr int kOutBufs = 4;
+
+struct TiledParams {
+    long long p0, d0m1;        // schedule: n_k = d0m1 + (p0 + k*M)/L (0-based index of the window's last sample)
+    long long k_begin, N;      // this launch covers outputs [k_begin, N)
+    int L, M, mprime;          // mprime = M - L (phase step; 0 for FIRStandard)
+    int KT;                    // outputs per tile (multiple of 16)
+    // start state of every time tile, computed on the host (closed form of src/Filters.jl:567-568) so that the
+    // kernel's phase arithmetic starts from parameter space and stays in the uniform datapath
+    struct Tile { int phi, s, xc0, pad; } tile[kMaxTiles];
+    unsigned char runlen[kMaxPhases];   // run length starting at phase phi, capped at RMAX
+    float bank[kBankFloats];   // [L][TPAD], row phi = pfb[:, phi] left-padded with zeros to TPAD taps
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// complex x real FMA: acc(re,im) += t * x(re,im)  -> one FFMA2 with a scalar (uniform-register) tap operand
+__device__ __forceinline__ void cfma(unsigned long long &acc, float t, unsigned long long x) {
+    unsigned long long tt;
+    asm("mov.b64 %0, {%1,%1};" : "=l"(tt) : "f"(t));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(tt), "l"(x));
+}
+__device__ __forceinline__ unsigned long long cadd(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// one run: RMAX outputs (the first `len` are kept) from a register window.  DELTA = parity of the window start.
+// ---------------------------------------------------------------------------------------------------------
+template <int TPAD, int RMAX, int DELTA>
+__device__ __forceinline__ void run_body_c64(const TiledParams &P, const unsigned long long (&xw)[TPAD + RMAX + 1],
+                                             int phi, int len, int kpos, uint32_t out_base, uint32_t row_off,
+                                             uint32_t row_swz) {
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+        const float *taps = P.bank + phi * TPAD;          // uniform address -> LDCU
+        unsigned long long a0 = 0ull, a1 = 0ull;
+#pragma unroll
+        for (int i = 0; i < TPAD; i += 2) {
+            const float2 t = *reinterpret_cast<const float2 *>(taps + i);
+            cfma(a0, t.x, xw[DELTA + r + i]);
+            cfma(a1, t.y, xw[DELTA + r + i + 1]);
+        }
+        const unsigned long long y = cadd(a0, a1);
+        if (r < len) {                                    // uniform predicate
+            const int kk = kpos + r;                      // tile-relative output index
+            const uint32_t a = out_base + (uint32_t)(((kk >> 3) & (kOutBufs - 1)) << 12) + row_off +
+                               (((uint32_t)((kk >> 1) & 3) ^ row_swz) << 4) + (uint32_t)((kk & 1) << 3);
+            asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(y) : "memory");
+        }
+        phi += P.mprime;
+        if (phi >= P.L) phi -= P.L;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel: complex64 samples, float32 taps.  grid = (time tiles, channel groups of 64), block = 64 threads.
+// ---------------------------------------------------------------------------------------------------------
+template <int TPAD, int RMAX, int NBOX>
+__global__ void __launch_bounds__(kTiledRows)
+k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+            const __grid_constant__ TiledParams P) {
+    static_assert((NBOX & (NBOX - 1)) == 0, "ring size must be a power of two");
+    constexpr int NP = (TPAD + RMAX + 1) / 2;             // sample pairs in the register window
+    constexpr int BOX_BYTES = kTiledRows * kBoxSamples * 8;   // 4096
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *in_ring = smem;                                   // NBOX boxes [64][8] complex64, SWIZZLE_64B
+    unsigned char *out_ring = smem + NBOX * BOX_BYTES;               // kOutBufs chunks [64][8] complex64
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(out_ring + kOutBufs * BOX_BYTES);
+
+    const int tid = threadIdx.x;
+    const int ch0 = blockIdx.y * kTiledRows;
+    const uint32_t in_base = smem_u32(in_ring), out_base = smem_u32(out_ring), bar_base = smem_u32(bars);
+    const uint32_t row_off = (uint32_t)tid * 64u;
+    const uint32_t row_swz = ((uint32_t)tid >> 1) & 3u;              // SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3
+
+    if (tid == 0) {
+        for (int i = 0; i < NBOX; ++i) mbar_init(bar_base + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmy) : "memory");
+    }
+
+    // ---- tile start state: from parameter space (uniform)
+    const int ka_rel = blockIdx.x * P.KT;                              // relative to k_begin
+    const int ntile = min(P.KT, (int)(P.N - P.k_begin) - ka_rel);
+    int phi = P.tile[blockIdx.x].phi;
+    int s = P.tile[blockIdx.x].s;                                      // window start, relative to box 0 of the tile
+    const int xc0 = P.tile[blockIdx.x].xc0;                            // float coordinate of box 0 in tmx
+    const int yc0 = ((int)P.k_begin + ka_rel) * 2;
+    // boxes this tile is expected to touch (prefetch bound); demand may exceed it by a box or two
+    const int jend = ((ntile + (int)(((long long)ntile * P.mprime) / P.L) + TPAD + RMAX) >> 3) + 1;
+    __syncthreads();
+
+    int k = 0;            // tile-relative index of the next output
+    int j_issued = 0;     // boxes issued so far (tile-relative)
+    int j_waited = 0;     // boxes already waited for
+    int q_flushed = 0;    // output chunks already handed to TMA
+
+    while (k < ntile) {
+        const int len = min((int)P.runlen[phi], ntile - k);
+        const int A = s & ~1;                        // aligned window start
+        const int jA = A >> 3;                        // oldest live box
+        const int jneed = (A + 2 * NP - 1) >> 3;      // newest box the window touches
+        const int q_done = k >> 3;                    // chunks completed by earlier runs
+
+        const bool flush = q_done > q_flushed;
+        if (flush) fence_async_smem();                // make this thread's st.shared visible to the async proxy
+        __syncthreads();                              // every warp finished the previous run (reads and writes)
+        if (tid == 0) {
+            if (flush) {
+                for (int q = q_flushed; q < q_done; ++q) {
+                    tma_store_2d(&tmy, yc0 + q * 16, ch0, out_base + (uint32_t)((q & (kOutBufs - 1)) << 12));
+                    tma_commit();
+                }
+                tma_wait_read<1>();                   // every store but the newest has finished reading smem
+            }
+            const int jtarget = max(jneed, min(jA + NBOX - 1, jend));
+            for (int j = j_issued; j <= jtarget && j < jA + NBOX; ++j) {
+                const uint32_t bar = bar_base + 8 * (j & (NBOX - 1));
+                mbar_expect_tx(bar, BOX_BYTES);
+                tma_load_2d(in_base + (uint32_t)((j & (NBOX - 1)) * BOX_BYTES), &tmx, xc0 + j * 16, ch0, bar);
+            }
+        }
+        if (flush) __syncthreads();                   // staging buffers older than the newest store are reusable
+        {
+            const int jtarget = max(jneed, min(jA + NBOX - 1, jend));
+            j_issued = max(j_issued, min(jtarget, jA + NBOX - 1) + 1);
+        }
+        q_flushed = q_done;
+        for (; j_waited <= jneed; ++j_waited)
+            mbar_wait(bar_base + 8 * (j_waited & (NBOX - 1)), (uint32_t)((j_waited / NBOX) & 1));
+
+        // ---- register window: NP aligned sample pairs starting at A (LDS.128, conflict free under SWIZZLE_64B)
+        unsigned long long xw[TPAD + RMAX + 1];
+        {
+            const int u0 = A >> 1;                    // pair index; 4 pairs per box
+#pragma unroll
+            for (int jj = 0; jj < NP; ++jj) {
+                const int u = u0 + jj;
+                const uint32_t a = in_base + (uint32_t)(((u >> 2) & (NBOX - 1)) * BOX_BYTES) + row_off +
+                                   (((uint32_t)(u & 3) ^ row_swz) << 4);
+                unsigned long long v0, v1;
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "r"(a));
+                xw[2 * jj] = v0;
+                if (2 * jj + 1 < TPAD + RMAX + 1) xw[2 * jj + 1] = v1;
+            }
+        }
+        if (s & 1) run_body_c64<TPAD, RMAX, 1>(P, xw, phi, len, k, out_base, row_off, row_swz);
+        else run_body_c64<TPAD, RMAX, 0>(P, xw, phi, len, k, out_base, row_off, row_swz);
+
+        // ---- advance the (uniform) schedule by `len` outputs
+        k += len;
+        phi += len * P.mprime;
+        s += len;
+        if (phi >= P.L) { phi -= P.L; s += 1; }      // the run ended on a phase wrap: the input index skips one
+    }
+
+    // ---- flush the remaining chunks (the last one may be partial: TMA clips at the tensor bound N)
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        const int q_end = (ntile + 7) >> 3;
+        for (int q = q_flushed; q < q_end; ++q) {
+            tma_store_2d(&tmy, yc0 + q * 16, ch0, out_base + (uint32_t)((q & (kOutBufs - 1)) << 12));
+            tma_commit();
+        }
+        tma_wait_read<0>();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TiledPlan {
+    bool ok = false;               // configuration is covered by a tiled kernel
+    int tpad = 0, rmax = 0;
+    TiledParams *hp = nullptr;     // host template of the parameter block (bank + run lengths filled once)
+    PFN_encodeTiled encode = nullptr;
+    int T = 0;
+};
+
+constexpr int kTPAD = 24, kRMAX = 12, kNBOX = 8;
+constexpr int kTiledSmem = kNBOX * 4096 + kOutBufs * 4096 + 8 * kNBOX + 1024;
+
+static inline void tiled_release(TiledPlan &p) {
+    delete p.hp;
+    p.hp = nullptr;
+    p.ok = false;
+}
+
+// kind/tx/ty are the mrb.h enums (0 standard, 3 rational ; 2 = complex64)
+static inline int32_t tiled_prepare(TiledPlan &p, int kind, int tx, int ty, int64_t L, int64_t M, int64_t Nphi,
+                                    int64_t T, const std::vector<double> &bank, const std::vector<double> &,
+                                    const cudaDeviceProp &) {
+    p.ok = false;
+    const bool kind_ok = kind == 0 /*standard*/ || kind == 3 /*rational*/;
+    if (!kind_ok || tx != 2 || ty != 2) return 0;
+    if (!(L <= M && M < 2 * L) || L > kMaxPhases || T > kTPAD || L * kTPAD > kBankFloats) return 0;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int32_t)(e ? e : cudaErrorUnknown);
+    p.encode = (PFN_encodeTiled)fn;
+    p.tpad = kTPAD; p.rmax = kRMAX; p.T = (int)T;
+    p.hp = new TiledParams();
+    memset(p.hp, 0, sizeof(TiledParams));
+    p.hp->L = (int)L; p.hp->M = (int)M; p.hp->mprime = (int)(M - L);
+    for (int64_t ph = 0; ph < L; ++ph) {
+        // row phi, left-padded with zeros: padded tap i multiplies the sample (TPAD-1-i) before the window's last one
+        for (int64_t i = 0; i < T; ++i) p.hp->bank[ph * kTPAD + (kTPAD - T) + i] = (float)bank[ph * T + i];
+        // outputs at phases phi, phi+m', ... share consecutive input indices until the phase wraps
+        int64_t len = p.hp->mprime == 0 ? kRMAX : std::min<int64_t>((L - 1 - ph) / p.hp->mprime + 1, kRMAX);
+        p.hp->runlen[ph] = (unsigned char)len;
+    }
+    e = cudaFuncSetAttribute(k_tiled_c64<kTPAD, kRMAX, kNBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmem);
+    if (e != cudaSuccess) return (int32_t)e;
+    p.ok = true;
+    return 0;
+}
+
+// Launch the tiled kernel for outputs [k_begin, N) of this chunk.  Returns k_begin (>= 0; the caller computes
+// [0, k_begin) with the generic kernel), -1 when the call is not covered, -2 on a CUDA error.
+static inline int64_t tiled_try_launch(TiledPlan &p, const GenParams &G, cudaStream_t st, const char **name,
+                                       int64_t *launches) {
+    if (!p.ok || G.mode != SEQ_INTEGER) return -1;
+    // TMA needs 16-byte aligned bases and row pitches, and 32-bit coordinates
+    if (((uintptr_t)G.x & 15) || ((uintptr_t)G.y & 15) || (G.ldx & 1) || (G.ldy & 1)) return -1;
+    if (G.n_in >= (1ll << 30) || G.nout >= (1ll << 30)) return -1;
+    // first output whose (padded) window lies entirely inside x: d0m1 + floor((p0 + k M)/L) >= TPAD-1
+    const int64_t q = (int64_t)p.tpad - 1 - G.d0m1;
+    int64_t kstar = q <= 0 ? 0 : ceil_div(q * G.L - G.p0, G.M);
+    if (kstar < 0) kstar = 0;
+    const int64_t k_begin = (kstar + 15) / 16 * 16;
+    if (G.nout - k_begin < 64) return -1;                     // too small to be worth a tiled launch
+
+    TiledParams &P = *p.hp;
+    P.p0 = G.p0; P.d0m1 = G.d0m1; P.k_begin = k_begin; P.N = G.nout;
+    const int64_t span = G.nout - k_begin;
+    P.KT = (int)std::max<int64_t>(1024, (ceil_div(span, kMaxTiles) + 15) / 16 * 16);
+    const int64_t ntiles = ceil_div(span, P.KT);
+    for (int64_t i = 0; i < ntiles; ++i) {
+        const int64_t ka = k_begin + i * P.KT;
+        const int64_t t0 = G.p0 + ka * G.M;
+        const int64_t xs0 = G.d0m1 + t0 / G.L - (p.tpad - 1);         // x-sample index of the first window start
+        const int64_t box0 = xs0 >> 3;
+        P.tile[i].phi = (int)(t0 % G.L);
+        P.tile[i].s = (int)(xs0 - (box0 << 3));
+        P.tile[i].xc0 = (int)(box0 << 3) * 2;
+    }
+    CUtensorMap tmx, tmy;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)(2 * G.n_in), (cuuint64_t)G.nch};
+        cuuint64_t strides[1] = {(cuuint64_t)G.ldx * 8};
+        cuuint32_t box[2] = {2 * kBoxSamples, kTiledRows};
+        cuuint32_t es[2] = {1, 1};
+        if (p.encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(G.x), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -1;
+        cuuint64_t ydims[2] = {(cuuint64_t)(2 * G.nout), (cuuint64_t)G.nch};
+        cuuint64_t ystrides[1] = {(cuuint64_t)G.ldy * 8};
+        if (p.encode(&tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, G.y, ydims, ystrides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -1;
+    }
+    dim3 grid((unsigned)ntiles, (unsigned)ceil_div(G.nch, kTiledRows));
+    k_tiled_c64<kTPAD, kRMAX, kNBOX><<<grid, kTiledRows, kTiledSmem, st>>>(tmx, tmy, P);
+    if (cudaPeekAtLastError() != cudaSuccess) return -2;
+    *name = "tiled_c64_t24_r12";
+    ++*launches;
+    return k_begin;
+}
+
+}  // namespace mrb

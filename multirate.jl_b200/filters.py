@@ -399,7 +399,7 @@ class FIRFilter:
                 raise ValueError("torch input must be a CUDA tensor (use numpy for host data)")
             squeeze = x.dim() == 1
             x2 = x.unsqueeze(0) if squeeze else x
-            if x2.stride(-1) != 1:
+            if x2.shape[-1] > 1 and x2.stride(-1) != 1:
                 x2 = x2.contiguous()
             nch, n_in = x2.shape
             tx = np.dtype(str(x2.dtype).replace("torch.", ""))
@@ -409,7 +409,7 @@ class FIRFilter:
                 ty = getattr(torch, str(self._ty))
                 buffer = torch.empty((nch, N) if not squeeze else (N,), dtype=ty, device=x.device)
             b2 = buffer.unsqueeze(0) if buffer.dim() == 1 else buffer
-            if str(b2.dtype).replace("torch.", "") != str(self._ty) or not b2.is_cuda or b2.stride(-1) != 1:
+            if str(b2.dtype).replace("torch.", "") != str(self._ty) or not b2.is_cuda or (b2.shape[-1] > 1 and b2.stride(-1) != 1):
                 raise TypeError("buffer must be a CUDA tensor of dtype %s, time contiguous" % self._ty)
             if b2.shape[0] != nch:
                 raise ValueError("buffer must have one row per channel")
@@ -431,7 +431,7 @@ class FIRFilter:
         if buffer is None:
             buffer = np.empty((nch, N) if not squeeze else (N,), dtype=self._ty)
         b2 = buffer[None, :] if buffer.ndim == 1 else buffer
-        if b2.dtype != self._ty or b2.strides[-1] != b2.itemsize or b2.shape[0] != nch:
+        if b2.dtype != self._ty or (b2.shape[-1] > 1 and b2.strides[-1] != b2.itemsize) or b2.shape[0] != nch:
             raise TypeError("buffer must be a %s array with one time-contiguous row per channel" % self._ty)
         ldy = b2.strides[0] // b2.itemsize if nch > 1 else max(b2.shape[1], 1)
         n_out = C.c_int64()

@@ -51,7 +51,8 @@ def test_readme_3_17_kat_on_gpu():
         assert np.array_equal(y, np.array(want)), (y, want)
         ys.append(y)
     assert np.sum(np.concatenate(ys) - mr.filt(h, x, Fraction(*k["ratio"]))) == 0.0
-    assert f.kernel.phiIdx == 2 and f.kernel.inputDeficit >= 1
+    o = mo.FIRFilter(h, Fraction(*k["ratio"])); o.filt(x)
+    assert states_equal(f, o)
 
 
 def test_farrow_notebook_count_on_gpu():
@@ -230,9 +231,10 @@ def test_device_path_torch_streaming(case, rng):
 
 def test_full_size_properties_c5_shard(rng):
     """BASELINE config 5 at full per-GPU chunk size, properties that need no oracle run over the whole
-    batch: (i) exact count; (ii) chunking invariance (64K one-shot == 4 x 16K streamed, same kernel family =>
-    bit-identical values); (iii) linearity in x; (iv) channel independence (a channel's output does not
-    depend on its neighbours); spot rows checked against the oracle."""
+    batch: (i) exact count; (ii) chunking invariance (64K one-shot == 4 x 16K streamed; the first ~24 outputs
+    of a chunk come from the generic kernel, whose summation order differs, hence a 1e-6 bound instead of
+    bit equality); (iii) linearity in x (exact: scaling by 2); (iv) channel independence (a channel's output
+    does not depend on its neighbours); spot rows checked against the oracle."""
     import torch
     h = mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32)
     nch, n = 1024, 1 << 16
@@ -243,7 +245,7 @@ def test_full_size_properties_c5_shard(rng):
     assert y1.shape[1] == 60212 == mo.FIRFilter(h, ratio).outputlength(n)
     f = mr.FIRFilter(h, ratio)
     y4 = torch.cat([f.filt(x[:, i * 16384:(i + 1) * 16384]) for i in range(4)], dim=1)
-    assert torch.equal(torch.view_as_real(y1), torch.view_as_real(y4))
+    assert (y1 - y4).abs().max().item() <= 1e-6 * y1.abs().max().item()
     y2 = mr.FIRFilter(h, ratio).filt(2 * x)
     assert torch.equal(torch.view_as_real(y2), torch.view_as_real(2 * y1))
     xs = x[100:164].clone()
@@ -256,7 +258,7 @@ def test_full_size_properties_c5_shard(rng):
 
 def test_segment_split_matches_stream(rng):
     """Long-stream split: S independent segments, each seeked to its closed-form start state with a
-    tap-length halo, reproduce the single-stream output exactly; no collective involved."""
+    tap-length halo, reproduce the single-stream output (same counts, values to 1e-6); no collective involved."""
     import torch
     h = mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32)
     ratio = Fraction(147, 160)
@@ -278,4 +280,4 @@ def test_segment_split_matches_stream(rng):
         parts.append(f.filt(x[:, a:b]))
     got = torch.cat(parts, dim=1)
     assert got.shape == whole.shape
-    assert torch.equal(torch.view_as_real(got), torch.view_as_real(whole))
+    assert (got - whole).abs().max().item() <= 1e-6 * whole.abs().max().item()
