@@ -2,7 +2,7 @@
 // (FIRStandard, and FIRRational with L <= M < 2L such as 147//160), complex64 or float32 samples.
 //
 // Mapping (B200, sm_100a), measured pipe rates in tools/ubench*.cu and DESIGN.md:
-//  * lane = channel.  A CTA is 2 warps = 64 channels; every thread walks the SAME outputs, so the whole
+//  * lane = channel.  A CTA is 64 channels x 2 run halves = 4 warps; every thread walks the SAME runs, so the whole
 //    phase / input-index bookkeeping (src/Filters.jl:567-568) is warp-uniform and lives in the uniform
 //    datapath (UIADD3 / UISETP), never in vector registers.
 //  * taps: the flipped phase-major bank (taps2pfb, src/Filters.jl:284-298) is a __grid_constant__ kernel
@@ -32,7 +32,8 @@
 
 namespace mrb {
 
-constexpr int kTiledRows = 64;          // channels per CTA (2 warps)
+constexpr int kTiledRows = 64;          // channels per CTA
+constexpr int kTiledThreads = 128;      // 4 warps: (channel half) x (run half)
 constexpr int kBoxSamples = 8;          // samples per TMA box row (64 B for complex64)
 constexpr int kBankFloats = 6144;       // tap bank capacity in kernel-parameter space (24 KiB)
 constexpr int kMaxTiles = 192;          // time tiles per launch (their start states ride in parameter space)
@@ -40,15 +41,24 @@ constexpr int kMaxPhases = 1024;
 constexpr int kOutBufs = 4;
 
 struct TiledParams {
-    long long p0, d0m1;        // schedule: n_k = d0m1 + (p0 + k*M)/L (0-based index of the window's last sample)
     long long k_begin, N;      // this launch covers outputs [k_begin, N)
-    int L, M, mprime;          // mprime = M - L (phase step; 0 for FIRStandard)
+    int L, M;
     int KT;                    // outputs per tile (multiple of 16)
-    // start state of every time tile, computed on the host (closed form of src/Filters.jl:567-568) so that the
-    // kernel's phase arithmetic starts from parameter space and stays in the uniform datapath
-    struct Tile { int phi, s, xc0, pad; } tile[kMaxTiles];
-    unsigned char runlen[kMaxPhases];   // run length starting at phase phi, capped at RMAX
-    float bank[kBankFloats];   // [L][TPAD], row phi = pfb[:, phi] left-padded with zeros to TPAD taps
+    int pad0;
+    // Start state of every time tile, computed on the host (closed form of src/Filters.jl:567-568) so that the
+    // kernel's sequencing starts from parameter space and stays in the uniform datapath.
+    //   j   : bank row of the tile's first output (rows are stored in RUN ORDER, see `bank`)
+    //   s   : x-sample index of its window start, relative to box 0 of the tile
+    //   xc0 : float coordinate of box 0 in the x tensor map
+    struct Tile { int j, s, xc0, pad; } tile[kMaxTiles];
+    // per bank row j: run length (bits 0-7, <= RMAX), "run ends on a phase wrap" (bit 8: the input index then
+    // skips one extra sample), row of the next run's first output (bits 16-31)
+    int runtab[kMaxPhases];
+    // Tap bank in RUN ORDER: row j holds branch phi_j = (j * (M-L)) mod L of the flipped phase-major bank
+    // (taps2pfb, src/Filters.jl:284-298), left-padded with zeros to TPAD taps; consecutive outputs of a run read
+    // consecutive rows, so every tap address inside a run is (one uniform base) + (compile-time offset).
+    // Rows L .. L+RMAX-2 repeat rows 0 .. RMAX-2.
+    float bank[kBankFloats];
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -99,29 +109,34 @@ __device__ __forceinline__ unsigned long long cadd(unsigned long long a, unsigne
 // ---------------------------------------------------------------------------------------------------------
 // one run: RMAX outputs (the first `len` are kept) from a register window.  DELTA = parity of the window start.
 // ---------------------------------------------------------------------------------------------------------
-template <int TPAD, int RMAX, int DELTA>
-__device__ __forceinline__ void run_body_c64(const TiledParams &P, const unsigned long long (&xw)[TPAD + RMAX + 1],
-                                             int phi, int len, int kpos, uint32_t out_base, uint32_t row_off,
+// RW = outputs per warp per run; R0 = first output of the run this warp computes (the run is split over the
+// two warps that share a channel group, which halves the shared-memory footprint per warp).
+template <int TPAD, int RW, int R0, int DELTA>
+__device__ __forceinline__ void run_body_c64(const TiledParams &P, const unsigned long long (&xw)[TPAD + RW + 1],
+                                             int j, int len, int kpos, uint32_t out_base, uint32_t row_off,
                                              uint32_t row_swz) {
+    const float *rows = P.bank + (j + R0) * TPAD;         // uniform base; everything below is base + constant
+    len -= R0;
+    kpos += R0;
 #pragma unroll
-    for (int r = 0; r < RMAX; ++r) {
-        const float *taps = P.bank + phi * TPAD;          // uniform address -> LDCU
-        unsigned long long a0 = 0ull, a1 = 0ull;
+    for (int r = 0; r < RW; ++r) {
+        unsigned long long a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;
 #pragma unroll
-        for (int i = 0; i < TPAD; i += 2) {
-            const float2 t = *reinterpret_cast<const float2 *>(taps + i);
-            cfma(a0, t.x, xw[DELTA + r + i]);
-            cfma(a1, t.y, xw[DELTA + r + i + 1]);
+        for (int i = 0; i < TPAD; i += 4) {
+            const float2 t0 = *reinterpret_cast<const float2 *>(rows + r * TPAD + i);
+            const float2 t1 = *reinterpret_cast<const float2 *>(rows + r * TPAD + i + 2);
+            cfma(a0, t0.x, xw[DELTA + r + i]);
+            cfma(a1, t0.y, xw[DELTA + r + i + 1]);
+            cfma(a2, t1.x, xw[DELTA + r + i + 2]);
+            cfma(a3, t1.y, xw[DELTA + r + i + 3]);
         }
-        const unsigned long long y = cadd(a0, a1);
+        const unsigned long long y = cadd(cadd(a0, a1), cadd(a2, a3));
         if (r < len) {                                    // uniform predicate
             const int kk = kpos + r;                      // tile-relative output index
             const uint32_t a = out_base + (uint32_t)(((kk >> 3) & (kOutBufs - 1)) << 12) + row_off +
                                (((uint32_t)((kk >> 1) & 3) ^ row_swz) << 4) + (uint32_t)((kk & 1) << 3);
             asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(y) : "memory");
         }
-        phi += P.mprime;
-        if (phi >= P.L) phi -= P.L;
     }
 }
 
@@ -129,11 +144,14 @@ __device__ __forceinline__ void run_body_c64(const TiledParams &P, const unsigne
 // kernel: complex64 samples, float32 taps.  grid = (time tiles, channel groups of 64), block = 64 threads.
 // ---------------------------------------------------------------------------------------------------------
 template <int TPAD, int RMAX, int NBOX>
-__global__ void __launch_bounds__(kTiledRows)
+__global__ void __launch_bounds__(kTiledThreads)
 k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
             const __grid_constant__ TiledParams P) {
     static_assert((NBOX & (NBOX - 1)) == 0, "ring size must be a power of two");
-    constexpr int NP = (TPAD + RMAX + 1) / 2;             // sample pairs in the register window
+    static_assert(RMAX % 4 == 0, "the run is split in two even halves");
+    constexpr int RW = RMAX / 2;                          // outputs per warp per run
+    constexpr int NP = (TPAD + RW + 1 + 1) / 2;           // sample pairs in a warp's register window
+    constexpr int NPRUN = (TPAD + RMAX + 1 + 1) / 2;      // sample pairs the whole run touches
     constexpr int BOX_BYTES = kTiledRows * kBoxSamples * 8;   // 4096
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *in_ring = smem;                                   // NBOX boxes [64][8] complex64, SWIZZLE_64B
@@ -143,8 +161,10 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     const int tid = threadIdx.x;
     const int ch0 = blockIdx.y * kTiledRows;
     const uint32_t in_base = smem_u32(in_ring), out_base = smem_u32(out_ring), bar_base = smem_u32(bars);
-    const uint32_t row_off = (uint32_t)tid * 64u;
-    const uint32_t row_swz = ((uint32_t)tid >> 1) & 3u;              // SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3
+    const int row = tid & (kTiledRows - 1);                          // channel within the group
+    const int half = tid >> 6;                                       // which half of every run this warp computes
+    const uint32_t row_off = (uint32_t)row * 64u;
+    const uint32_t row_swz = ((uint32_t)row >> 1) & 3u;              // SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3
 
     if (tid == 0) {
         for (int i = 0; i < NBOX; ++i) mbar_init(bar_base + 8 * i, 1);
@@ -156,12 +176,12 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     // ---- tile start state: from parameter space (uniform)
     const int ka_rel = blockIdx.x * P.KT;                              // relative to k_begin
     const int ntile = min(P.KT, (int)(P.N - P.k_begin) - ka_rel);
-    int phi = P.tile[blockIdx.x].phi;
+    int j = P.tile[blockIdx.x].j;                                      // bank row (run order) of the next output
     int s = P.tile[blockIdx.x].s;                                      // window start, relative to box 0 of the tile
     const int xc0 = P.tile[blockIdx.x].xc0;                            // float coordinate of box 0 in tmx
     const int yc0 = ((int)P.k_begin + ka_rel) * 2;
     // boxes this tile is expected to touch (prefetch bound); demand may exceed it by a box or two
-    const int jend = ((ntile + (int)(((long long)ntile * P.mprime) / P.L) + TPAD + RMAX) >> 3) + 1;
+    const int jend = ((ntile + (int)(((long long)ntile * (P.M - P.L)) / P.L) + TPAD + RMAX) >> 3) + 1;
     __syncthreads();
 
     int k = 0;            // tile-relative index of the next output
@@ -170,10 +190,11 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     int q_flushed = 0;    // output chunks already handed to TMA
 
     while (k < ntile) {
-        const int len = min((int)P.runlen[phi], ntile - k);
+        const int rt = P.runtab[j];
+        const int len = min(rt & 0xff, ntile - k);
         const int A = s & ~1;                        // aligned window start
         const int jA = A >> 3;                        // oldest live box
-        const int jneed = (A + 2 * NP - 1) >> 3;      // newest box the window touches
+        const int jneed = (A + 2 * NPRUN - 1) >> 3;   // newest box the run's windows touch
         const int q_done = k >> 3;                    // chunks completed by earlier runs
 
         const bool flush = q_done > q_flushed;
@@ -204,9 +225,9 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
             mbar_wait(bar_base + 8 * (j_waited & (NBOX - 1)), (uint32_t)((j_waited / NBOX) & 1));
 
         // ---- register window: NP aligned sample pairs starting at A (LDS.128, conflict free under SWIZZLE_64B)
-        unsigned long long xw[TPAD + RMAX + 1];
+        unsigned long long xw[TPAD + RW + 1];
         {
-            const int u0 = A >> 1;                    // pair index; 4 pairs per box
+            const int u0 = (A >> 1) + half * (RW / 2);   // pair index of this warp's window; 4 pairs per box
 #pragma unroll
             for (int jj = 0; jj < NP; ++jj) {
                 const int u = u0 + jj;
@@ -215,17 +236,21 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                 unsigned long long v0, v1;
                 asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "r"(a));
                 xw[2 * jj] = v0;
-                if (2 * jj + 1 < TPAD + RMAX + 1) xw[2 * jj + 1] = v1;
+                if (2 * jj + 1 < TPAD + RW + 1) xw[2 * jj + 1] = v1;
             }
         }
-        if (s & 1) run_body_c64<TPAD, RMAX, 1>(P, xw, phi, len, k, out_base, row_off, row_swz);
-        else run_body_c64<TPAD, RMAX, 0>(P, xw, phi, len, k, out_base, row_off, row_swz);
+        if (half == 0) {
+            if (s & 1) run_body_c64<TPAD, RW, 0, 1>(P, xw, j, len, k, out_base, row_off, row_swz);
+            else run_body_c64<TPAD, RW, 0, 0>(P, xw, j, len, k, out_base, row_off, row_swz);
+        } else {
+            if (s & 1) run_body_c64<TPAD, RW, RW, 1>(P, xw, j, len, k, out_base, row_off, row_swz);
+            else run_body_c64<TPAD, RW, RW, 0>(P, xw, j, len, k, out_base, row_off, row_swz);
+        }
 
         // ---- advance the (uniform) schedule by `len` outputs
         k += len;
-        phi += len * P.mprime;
-        s += len;
-        if (phi >= P.L) { phi -= P.L; s += 1; }      // the run ended on a phase wrap: the input index skips one
+        s += len + ((rt >> 8) & 1);                  // the run ended on a phase wrap: the input index skips one
+        j = rt >> 16;
     }
 
     // ---- flush the remaining chunks (the last one may be partial: TMA clips at the tensor bound N)
@@ -254,6 +279,7 @@ struct TiledPlan {
     TiledParams *hp = nullptr;     // host template of the parameter block (bank + run lengths filled once)
     PFN_encodeTiled encode = nullptr;
     int T = 0;
+    std::vector<int> row_of_phase;
 };
 
 constexpr int kTPAD = 24, kRMAX = 12, kNBOX = 8;
@@ -272,7 +298,7 @@ static inline int32_t tiled_prepare(TiledPlan &p, int kind, int tx, int ty, int6
     p.ok = false;
     const bool kind_ok = kind == 0 /*standard*/ || kind == 3 /*rational*/;
     if (!kind_ok || tx != 2 || ty != 2) return 0;
-    if (!(L <= M && M < 2 * L) || L > kMaxPhases || T > kTPAD || L * kTPAD > kBankFloats) return 0;
+    if (!(L <= M && M < 2 * L) || L > kMaxPhases || T > kTPAD || (L + kRMAX) * kTPAD > kBankFloats) return 0;
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -281,13 +307,26 @@ static inline int32_t tiled_prepare(TiledPlan &p, int kind, int tx, int ty, int6
     p.tpad = kTPAD; p.rmax = kRMAX; p.T = (int)T;
     p.hp = new TiledParams();
     memset(p.hp, 0, sizeof(TiledParams));
-    p.hp->L = (int)L; p.hp->M = (int)M; p.hp->mprime = (int)(M - L);
-    for (int64_t ph = 0; ph < L; ++ph) {
-        // row phi, left-padded with zeros: padded tap i multiplies the sample (TPAD-1-i) before the window's last one
-        for (int64_t i = 0; i < T; ++i) p.hp->bank[ph * kTPAD + (kTPAD - T) + i] = (float)bank[ph * T + i];
-        // outputs at phases phi, phi+m', ... share consecutive input indices until the phase wraps
-        int64_t len = p.hp->mprime == 0 ? kRMAX : std::min<int64_t>((L - 1 - ph) / p.hp->mprime + 1, kRMAX);
-        p.hp->runlen[ph] = (unsigned char)len;
+    p.hp->L = (int)L; p.hp->M = (int)M;
+    const int64_t mp = M - L;                                          // phase step per output
+    p.row_of_phase.assign((size_t)L, 0);
+    std::vector<int64_t> phase_of_row((size_t)L);
+    for (int64_t j = 0; j < L; ++j) {
+        phase_of_row[j] = (j * mp) % L;                                // a bijection: gcd(M-L, L) == gcd(M, L) == 1
+        p.row_of_phase[phase_of_row[j]] = (int)j;
+    }
+    for (int64_t j = 0; j < L + kRMAX - 1; ++j) {
+        const int64_t ph = phase_of_row[j % L];
+        // row, left-padded with zeros: padded tap i multiplies the sample (TPAD-1-i) before the window's last one
+        for (int64_t i = 0; i < T; ++i) p.hp->bank[j * kTPAD + (kTPAD - T) + i] = (float)bank[ph * T + i];
+    }
+    for (int64_t j = 0; j < L; ++j) {
+        const int64_t ph = phase_of_row[j];
+        // outputs at phases ph, ph+mp, ... read consecutive input windows until the phase wraps past L
+        const int64_t to_wrap = mp == 0 ? kRMAX : (L - 1 - ph) / mp + 1;
+        const int64_t len = std::min<int64_t>(to_wrap, kRMAX);
+        const int64_t wrap = (mp != 0 && len == to_wrap) ? 1 : 0;
+        p.hp->runtab[j] = (int)(len | (wrap << 8) | (((j + len) % L) << 16));
     }
     e = cudaFuncSetAttribute(k_tiled_c64<kTPAD, kRMAX, kNBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmem);
     if (e != cudaSuccess) return (int32_t)e;
@@ -311,7 +350,7 @@ static inline int64_t tiled_try_launch(TiledPlan &p, const GenParams &G, cudaStr
     if (G.nout - k_begin < 64) return -1;                     // too small to be worth a tiled launch
 
     TiledParams &P = *p.hp;
-    P.p0 = G.p0; P.d0m1 = G.d0m1; P.k_begin = k_begin; P.N = G.nout;
+    P.k_begin = k_begin; P.N = G.nout;
     const int64_t span = G.nout - k_begin;
     P.KT = (int)std::max<int64_t>(1024, (ceil_div(span, kMaxTiles) + 15) / 16 * 16);
     const int64_t ntiles = ceil_div(span, P.KT);
@@ -320,7 +359,7 @@ static inline int64_t tiled_try_launch(TiledPlan &p, const GenParams &G, cudaStr
         const int64_t t0 = G.p0 + ka * G.M;
         const int64_t xs0 = G.d0m1 + t0 / G.L - (p.tpad - 1);         // x-sample index of the first window start
         const int64_t box0 = xs0 >> 3;
-        P.tile[i].phi = (int)(t0 % G.L);
+        P.tile[i].j = p.row_of_phase[(size_t)(t0 % G.L)];
         P.tile[i].s = (int)(xs0 - (box0 << 3));
         P.tile[i].xc0 = (int)(box0 << 3) * 2;
     }
@@ -342,7 +381,7 @@ static inline int64_t tiled_try_launch(TiledPlan &p, const GenParams &G, cudaStr
             return -1;
     }
     dim3 grid((unsigned)ntiles, (unsigned)ceil_div(G.nch, kTiledRows));
-    k_tiled_c64<kTPAD, kRMAX, kNBOX><<<grid, kTiledRows, kTiledSmem, st>>>(tmx, tmy, P);
+    k_tiled_c64<kTPAD, kRMAX, kNBOX><<<grid, kTiledThreads, kTiledSmem, st>>>(tmx, tmy, P);
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
     *name = "tiled_c64_t24_r12";
     ++*launches;
