@@ -38,7 +38,8 @@ constexpr int kBoxSamples = 8;          // samples per TMA box row (64 B for com
 constexpr int kBankFloats = 6144;       // tap bank capacity in kernel-parameter space (24 KiB)
 constexpr int kMaxTiles = 192;          // time tiles per launch (their start states ride in parameter space)
 constexpr int kMaxPhases = 1024;
-constexpr int kOutBufs = 4;
+constexpr int kOutBufs = 8;             // staging buffers of kOutChunk outputs each
+constexpr int kOutChunk = 4;            // outputs per staged TMA store (32-byte rows, SWIZZLE_32B)
 
 struct TiledParams {
     long long k_begin, N;      // this launch covers outputs [k_begin, N)
@@ -113,8 +114,7 @@ __device__ __forceinline__ unsigned long long cadd(unsigned long long a, unsigne
 // two warps that share a channel group, which halves the shared-memory footprint per warp).
 template <int TPAD, int RW, int R0, int DELTA>
 __device__ __forceinline__ void run_body_c64(const TiledParams &P, const unsigned long long (&xw)[TPAD + RW + 1],
-                                             int j, int len, int kpos, uint32_t out_base, uint32_t row_off,
-                                             uint32_t row_swz) {
+                                             int j, int len, int kpos, uint32_t obase_x) {
     const float *rows = P.bank + (j + R0) * TPAD;         // uniform base; everything below is base + constant
     len -= R0;
     kpos += R0;
@@ -133,8 +133,8 @@ __device__ __forceinline__ void run_body_c64(const TiledParams &P, const unsigne
         const unsigned long long y = cadd(cadd(a0, a1), cadd(a2, a3));
         if (r < len) {                                    // uniform predicate
             const int kk = kpos + r;                      // tile-relative output index
-            const uint32_t a = out_base + (uint32_t)(((kk >> 3) & (kOutBufs - 1)) << 12) + row_off +
-                               (((uint32_t)((kk >> 1) & 3) ^ row_swz) << 4) + (uint32_t)((kk & 1) << 3);
+            const uint32_t a = (obase_x ^ (uint32_t)(((kk >> 1) & 1) << 4)) +
+                               (uint32_t)((((kk >> 2) & (kOutBufs - 1)) << 11) + ((kk & 1) << 3));
             asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(y) : "memory");
         }
     }
@@ -155,16 +155,19 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     constexpr int BOX_BYTES = kTiledRows * kBoxSamples * 8;   // 4096
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *in_ring = smem;                                   // NBOX boxes [64][8] complex64, SWIZZLE_64B
-    unsigned char *out_ring = smem + NBOX * BOX_BYTES;               // kOutBufs chunks [64][8] complex64
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(out_ring + kOutBufs * BOX_BYTES);
+    unsigned char *out_ring = smem + NBOX * BOX_BYTES;               // kOutBufs chunks [64][4] complex64, SWIZZLE_32B
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(out_ring + kOutBufs * 2048);
 
     const int tid = threadIdx.x;
     const int ch0 = blockIdx.y * kTiledRows;
     const uint32_t in_base = smem_u32(in_ring), out_base = smem_u32(out_ring), bar_base = smem_u32(bars);
     const int row = tid & (kTiledRows - 1);                          // channel within the group
     const int half = tid >> 6;                                       // which half of every run this warp computes
-    const uint32_t row_off = (uint32_t)row * 64u;
-    const uint32_t row_swz = ((uint32_t)row >> 1) & 3u;              // SWIZZLE_64B: 16-byte chunk ^= (row>>1)&3
+    // SWIZZLE_64B: the 16-byte chunk index is XORed with (row>>1)&3.  Fold the per-thread part into the bases,
+    // so that every shared-memory address is (per-thread base ^ uniform chunk bits) + uniform offset.
+    const uint32_t row_swz4 = (((uint32_t)row >> 1) & 3u) << 4;
+    const uint32_t ibase_x = (in_base + (uint32_t)row * 64u) ^ row_swz4;
+    const uint32_t obase_x = (out_base + (uint32_t)row * 32u) ^ ((((uint32_t)row >> 2) & 1u) << 4);   // SWIZZLE_32B
 
     if (tid == 0) {
         for (int i = 0; i < NBOX; ++i) mbar_init(bar_base + 8 * i, 1);
@@ -195,7 +198,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         const int A = s & ~1;                        // aligned window start
         const int jA = A >> 3;                        // oldest live box
         const int jneed = (A + 2 * NPRUN - 1) >> 3;   // newest box the run's windows touch
-        const int q_done = k >> 3;                    // chunks completed by earlier runs
+        const int q_done = k >> 2;                    // chunks completed by earlier runs
 
         const bool flush = q_done > q_flushed;
         if (flush) fence_async_smem();                // make this thread's st.shared visible to the async proxy
@@ -203,10 +206,13 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         if (tid == 0) {
             if (flush) {
                 for (int q = q_flushed; q < q_done; ++q) {
-                    tma_store_2d(&tmy, yc0 + q * 16, ch0, out_base + (uint32_t)((q & (kOutBufs - 1)) << 12));
+                    tma_store_2d(&tmy, yc0 + q * 8, ch0, out_base + (uint32_t)((q & (kOutBufs - 1)) << 11));
                     tma_commit();
                 }
-                tma_wait_read<1>();                   // every store but the newest has finished reading smem
+                // Every store but the newest has finished reading its staging buffer.  A run completes at most 3
+                // chunks and writes into at most 4, so with 8 buffers the compute warps never reach a buffer
+                // whose store is still unconfirmed at the barrier above: no second barrier is needed.
+                tma_wait_read<1>();
             }
             const int jtarget = max(jneed, min(jA + NBOX - 1, jend));
             for (int j = j_issued; j <= jtarget && j < jA + NBOX; ++j) {
@@ -215,7 +221,6 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                 tma_load_2d(in_base + (uint32_t)((j & (NBOX - 1)) * BOX_BYTES), &tmx, xc0 + j * 16, ch0, bar);
             }
         }
-        if (flush) __syncthreads();                   // staging buffers older than the newest store are reusable
         {
             const int jtarget = max(jneed, min(jA + NBOX - 1, jend));
             j_issued = max(j_issued, min(jtarget, jA + NBOX - 1) + 1);
@@ -231,8 +236,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 #pragma unroll
             for (int jj = 0; jj < NP; ++jj) {
                 const int u = u0 + jj;
-                const uint32_t a = in_base + (uint32_t)(((u >> 2) & (NBOX - 1)) * BOX_BYTES) + row_off +
-                                   (((uint32_t)(u & 3) ^ row_swz) << 4);
+                const uint32_t a = (ibase_x ^ (uint32_t)((u & 3) << 4)) + (uint32_t)(((u >> 2) & (NBOX - 1)) * BOX_BYTES);
                 unsigned long long v0, v1;
                 asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "r"(a));
                 xw[2 * jj] = v0;
@@ -240,11 +244,11 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
             }
         }
         if (half == 0) {
-            if (s & 1) run_body_c64<TPAD, RW, 0, 1>(P, xw, j, len, k, out_base, row_off, row_swz);
-            else run_body_c64<TPAD, RW, 0, 0>(P, xw, j, len, k, out_base, row_off, row_swz);
+            if (s & 1) run_body_c64<TPAD, RW, 0, 1>(P, xw, j, len, k, obase_x);
+            else run_body_c64<TPAD, RW, 0, 0>(P, xw, j, len, k, obase_x);
         } else {
-            if (s & 1) run_body_c64<TPAD, RW, RW, 1>(P, xw, j, len, k, out_base, row_off, row_swz);
-            else run_body_c64<TPAD, RW, RW, 0>(P, xw, j, len, k, out_base, row_off, row_swz);
+            if (s & 1) run_body_c64<TPAD, RW, RW, 1>(P, xw, j, len, k, obase_x);
+            else run_body_c64<TPAD, RW, RW, 0>(P, xw, j, len, k, obase_x);
         }
 
         // ---- advance the (uniform) schedule by `len` outputs
@@ -257,9 +261,9 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-        const int q_end = (ntile + 7) >> 3;
+        const int q_end = (ntile + kOutChunk - 1) >> 2;
         for (int q = q_flushed; q < q_end; ++q) {
-            tma_store_2d(&tmy, yc0 + q * 16, ch0, out_base + (uint32_t)((q & (kOutBufs - 1)) << 12));
+            tma_store_2d(&tmy, yc0 + q * 8, ch0, out_base + (uint32_t)((q & (kOutBufs - 1)) << 11));
             tma_commit();
         }
         tma_wait_read<0>();
@@ -283,7 +287,7 @@ struct TiledPlan {
 };
 
 constexpr int kTPAD = 24, kRMAX = 12, kNBOX = 8;
-constexpr int kTiledSmem = kNBOX * 4096 + kOutBufs * 4096 + 8 * kNBOX + 1024;
+constexpr int kTiledSmem = kNBOX * 4096 + kOutBufs * 2048 + 8 * kNBOX + 1024;
 
 static inline void tiled_release(TiledPlan &p) {
     delete p.hp;
@@ -375,8 +379,9 @@ static inline int64_t tiled_try_launch(TiledPlan &p, const GenParams &G, cudaStr
             return -1;
         cuuint64_t ydims[2] = {(cuuint64_t)(2 * G.nout), (cuuint64_t)G.nch};
         cuuint64_t ystrides[1] = {(cuuint64_t)G.ldy * 8};
-        if (p.encode(&tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, G.y, ydims, ystrides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+        cuuint32_t ybox[2] = {2 * kOutChunk, kTiledRows};
+        if (p.encode(&tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, G.y, ydims, ystrides, ybox, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return -1;
     }
