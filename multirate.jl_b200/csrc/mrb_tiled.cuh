@@ -112,9 +112,22 @@ __device__ __forceinline__ unsigned long long cadd(unsigned long long a, unsigne
 // ---------------------------------------------------------------------------------------------------------
 // RW = outputs per warp per run; R0 = first output of the run this warp computes (the run is split over the
 // two warps that share a channel group, which halves the shared-memory footprint per warp).
-template <int TPAD, int RW, int R0, int DELTA>
-__device__ __forceinline__ void run_body_c64(const TiledParams &P, const unsigned long long (&xw)[TPAD + RW + 1],
-                                             int j, int len, int kpos, uint32_t obase_x) {
+template <int TPAD, int RW, int R0, int DELTA, int NBOX>
+__device__ __forceinline__ void run_body_c64(const TiledParams &P, int A, uint32_t ibase_x, int j, int len, int kpos,
+                                             uint32_t obase_x) {
+    // ---- register window: NP aligned sample pairs (LDS.128, conflict free under SWIZZLE_64B).  Every index
+    // below is uniform, so the only per-thread work per load is one XOR with the folded base.
+    constexpr int NP = (TPAD + RW + 1 + 1) / 2;
+    unsigned long long xw[2 * NP];
+    {
+        const int u0 = (A >> 1) + R0 / 2;                 // pair index of this warp's window; 4 pairs per box
+#pragma unroll
+        for (int jj = 0; jj < NP; ++jj) {
+            const int u = u0 + jj;
+            const uint32_t a = (ibase_x ^ (uint32_t)((u & 3) << 4)) + (uint32_t)(((u >> 2) & (NBOX - 1)) << 12);
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xw[2 * jj]), "=l"(xw[2 * jj + 1]) : "r"(a));
+        }
+    }
     const float *rows = P.bank + (j + R0) * TPAD;         // uniform base; everything below is base + constant
     len -= R0;
     kpos += R0;
@@ -150,7 +163,6 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     static_assert((NBOX & (NBOX - 1)) == 0, "ring size must be a power of two");
     static_assert(RMAX % 4 == 0, "the run is split in two even halves");
     constexpr int RW = RMAX / 2;                          // outputs per warp per run
-    constexpr int NP = (TPAD + RW + 1 + 1) / 2;           // sample pairs in a warp's register window
     constexpr int NPRUN = (TPAD + RMAX + 1 + 1) / 2;      // sample pairs the whole run touches
     constexpr int BOX_BYTES = kTiledRows * kBoxSamples * 8;   // 4096
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -229,26 +241,12 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         for (; j_waited <= jneed; ++j_waited)
             mbar_wait(bar_base + 8 * (j_waited & (NBOX - 1)), (uint32_t)((j_waited / NBOX) & 1));
 
-        // ---- register window: NP aligned sample pairs starting at A (LDS.128, conflict free under SWIZZLE_64B)
-        unsigned long long xw[TPAD + RW + 1];
-        {
-            const int u0 = (A >> 1) + half * (RW / 2);   // pair index of this warp's window; 4 pairs per box
-#pragma unroll
-            for (int jj = 0; jj < NP; ++jj) {
-                const int u = u0 + jj;
-                const uint32_t a = (ibase_x ^ (uint32_t)((u & 3) << 4)) + (uint32_t)(((u >> 2) & (NBOX - 1)) * BOX_BYTES);
-                unsigned long long v0, v1;
-                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "r"(a));
-                xw[2 * jj] = v0;
-                if (2 * jj + 1 < TPAD + RW + 1) xw[2 * jj + 1] = v1;
-            }
-        }
         if (half == 0) {
-            if (s & 1) run_body_c64<TPAD, RW, 0, 1>(P, xw, j, len, k, obase_x);
-            else run_body_c64<TPAD, RW, 0, 0>(P, xw, j, len, k, obase_x);
+            if (s & 1) run_body_c64<TPAD, RW, 0, 1, NBOX>(P, A, ibase_x, j, len, k, obase_x);
+            else run_body_c64<TPAD, RW, 0, 0, NBOX>(P, A, ibase_x, j, len, k, obase_x);
         } else {
-            if (s & 1) run_body_c64<TPAD, RW, RW, 1>(P, xw, j, len, k, obase_x);
-            else run_body_c64<TPAD, RW, RW, 0>(P, xw, j, len, k, obase_x);
+            if (s & 1) run_body_c64<TPAD, RW, RW, 1, NBOX>(P, A, ibase_x, j, len, k, obase_x);
+            else run_body_c64<TPAD, RW, RW, 0, NBOX>(P, A, ibase_x, j, len, k, obase_x);
         }
 
         // ---- advance the (uniform) schedule by `len` outputs
