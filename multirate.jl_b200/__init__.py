@@ -8,10 +8,11 @@ The directory name contains a dot, so import it through the repo-root shim:
 """
 from . import _ffi
 from ._ffi import MrbError, build
+from .sharding import channel_shard, segment_bounds, segment_plan
 from .filters import (FIRArbitrary, FIRDecimator, FIRFarrow, FIRFilter, FIRInterpolator, FIRKernel, FIRRational,
                       FIRStandard, filt, filt_, inputlength, nextphase, outputlength, pfb2pnfb, polyfit, reset,
                       setphase, taps2pfb, tapsforphase, tapsforphase_)
 
 __all__ = ["FIRFilter", "FIRKernel", "FIRStandard", "FIRInterpolator", "FIRDecimator", "FIRRational", "FIRArbitrary",
            "FIRFarrow", "filt", "filt_", "reset", "setphase", "outputlength", "inputlength", "taps2pfb", "tapsforphase",
-           "tapsforphase_", "nextphase", "polyfit", "pfb2pnfb", "MrbError", "build"]
+           "tapsforphase_", "nextphase", "polyfit", "pfb2pnfb", "MrbError", "build", "channel_shard", "segment_bounds", "segment_plan"]

@@ -216,6 +216,13 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         if (flush) fence_async_smem();                // make this thread's st.shared visible to the async proxy
         __syncthreads();                              // every warp finished the previous run (reads and writes)
         if (tid == 0) {
+            // loads first: they are on the critical path of the NEXT run; the stores only have to leave eventually
+            const int jtarget = max(jneed, min(jA + NBOX - 1, jend));
+            for (int j = j_issued; j <= jtarget && j < jA + NBOX; ++j) {
+                const uint32_t bar = bar_base + 8 * (j & (NBOX - 1));
+                mbar_expect_tx(bar, BOX_BYTES);
+                tma_load_2d(in_base + (uint32_t)((j & (NBOX - 1)) * BOX_BYTES), &tmx, xc0 + j * 16, ch0, bar);
+            }
             if (flush) {
                 for (int q = q_flushed; q < q_done; ++q) {
                     tma_store_2d(&tmy, yc0 + q * 8, ch0, out_base + (uint32_t)((q & (kOutBufs - 1)) << 11));
@@ -225,12 +232,6 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                 // chunks and writes into at most 4, so with 8 buffers the compute warps never reach a buffer
                 // whose store is still unconfirmed at the barrier above: no second barrier is needed.
                 tma_wait_read<1>();
-            }
-            const int jtarget = max(jneed, min(jA + NBOX - 1, jend));
-            for (int j = j_issued; j <= jtarget && j < jA + NBOX; ++j) {
-                const uint32_t bar = bar_base + 8 * (j & (NBOX - 1));
-                mbar_expect_tx(bar, BOX_BYTES);
-                tma_load_2d(in_base + (uint32_t)((j & (NBOX - 1)) * BOX_BYTES), &tmx, xc0 + j * 16, ch0, bar);
             }
         }
         {

@@ -69,3 +69,21 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "multirate_oracle" not in txt and "mr_oracle" not in txt and "c_oracle" not in txt, fn
+
+
+def test_tiled_kernel_uses_uniform_datapath_taps_tma_and_ffma2():
+    """The headline kernel's design rests on three SASS facts: taps arrive through the uniform
+    datapath (LDCU, not vector LDC -- ptxas picks heuristically, so it is pinned here), samples and results move
+    by TMA (UTMALDG / UTMASTG), and the complex x real FMA is a packed FFMA2."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    out = subprocess.run([cuobjdump, "-sass", mr._ffi.LIB], capture_output=True, text=True).stdout
+    body = out[out.index("k_tiled_c64"):]
+    nxt = body.find("Function :", 10)
+    body = body[:nxt] if nxt > 0 else body
+    n_ldcu = len(re.findall(r"\bLDCU(\.64)? UR\d+, c\[0x0\]\[UR", body))
+    n_ldc_vec = len(re.findall(r"\bLDC(\.64)? R\d+, c\[0x0\]\[R", body))
+    assert len(re.findall(r"\bFFMA2\b", body)) >= 288
+    assert n_ldcu >= 200 and n_ldc_vec <= 8, (n_ldcu, n_ldc_vec)
+    assert "UTMALDG" in body and "UTMASTG" in body
