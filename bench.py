@@ -245,7 +245,7 @@ def main():
         x = torch.view_as_complex(torch.rand((nch, n, 2), generator=gen, device="cuda", dtype=torch.float32))
     else:
         x = torch.rand((nch, n), generator=gen, device="cuda", dtype=torch.float32)
-    n_out_max = f.outputlength(n) + 2
+    n_out_max = (f.outputlength(n) + 2 + 3) // 4 * 4                  # row pitch: a multiple of 16 bytes (TMA)
     ybuf = torch.empty((nch, n_out_max), dtype=x.dtype, device="cuda")
     es = x.element_size()
 

@@ -281,3 +281,31 @@ def test_segment_split_matches_stream(rng):
     got = torch.cat(parts, dim=1)
     assert got.shape == whole.shape
     assert (got - whole).abs().max().item() <= 1e-6 * whole.abs().max().item()
+
+
+@pytest.mark.parametrize("L,ntaps,nch", [(1, 128, 33), (1, 97, 5), (1, 31, 64), (2, 200, 40), (2, 66, 1), (4, 512, 31),
+                                          (4, 390, 96)])
+def test_unit_stride_f32_kernel_shapes(L, ntaps, nch, rng):
+    """The float32 standard / interpolator fast path (mrb_unit.cuh): ragged tap counts (zero-padded tap blocks),
+    ragged channel counts (TMA clips rows), chunk lengths that are not whole steps, state carried across
+    chunks; against the oracle and the generic kernel."""
+    import torch
+    h = rng.standard_normal(ntaps).astype(np.float32)
+    ratio = Fraction(L, 1)
+    n = 5000                                                          # row pitch: a multiple of 16 bytes (TMA)
+    x = rand_samples(rng, (nch, n), np.float32)
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, ratio)
+    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=np.float32)
+    g.set_kernel_policy(1)
+    o = mo.FIRFilter(h, ratio)
+    for a, b in ((0, 2048), (2048, 2052), (2052, 4001), (4001, 4008), (4008, n)):   # 4001: misaligned -> generic
+        yd = f.filt(xd[:, a:b])
+        yg = g.filt(xd[:, a:b])
+        w = o.filt(x[: min(nch, 3), a:b])
+        torch.cuda.synchronize()
+        y = yd.cpu().numpy()
+        assert y.shape == (nch, (b - a) * L)
+        assert nerr(y[: min(nch, 3)], w) <= 1e-5
+        assert nerr(yg.cpu().numpy(), y) <= 2e-6
+    assert f.last_kernel.startswith("unit_f32"), f.last_kernel
