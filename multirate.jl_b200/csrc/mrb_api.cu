@@ -17,6 +17,7 @@
 #include "mrb_seq.h"
 #include "mrb_tiled.cuh"
 #include "mrb_unit.cuh"
+#include "mrb_decim.cuh"
 
 using namespace mrb;
 
@@ -87,6 +88,7 @@ struct mrb_filter {
     cudaStream_t own_stream = nullptr;
     TiledPlan tiled;                   // fast-path resources (mrb_tiled.cuh)
     UnitPlan unit;                     // fast path for float32 standard / interpolator (mrb_unit.cuh)
+    DecPlan decim;                     // fast path for complex64 decimators (mrb_decim.cuh)
     int policy = 0;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // one pair per timed mrb_filt
@@ -109,6 +111,7 @@ static void free_device(mrb_filter *f) {
     cudaFree(f->d_taptab); cudaFree(f->d_xs); cudaFree(f->d_ys);
     tiled_release(f->tiled);
     unit_release(f->unit);
+    decim_release(f->decim);
     for (auto &p : f->tev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (f->own_stream) cudaStreamDestroy(f->own_stream);
 }
@@ -223,6 +226,8 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
         if (rc != 0) return fail(MRB_ERR_CUDA, "tiled_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
         rc = unit_prepare(f->unit, kind, f->tx, f->ty, f->L, f->M, f->T, f->bank, prop);
         if (rc != 0) return fail(MRB_ERR_CUDA, "unit_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
+        rc = decim_prepare(f->decim, kind, f->tx, f->ty, f->L, f->M, f->T, f->bank, prop);
+        if (rc != 0) return fail(MRB_ERR_CUDA, "decim_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
         CU(cudaDeviceSynchronize());
     }
     *out = f.release();
@@ -529,6 +534,7 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
             if (f->policy == 0) {
                 k_begin = tiled_try_launch(f->tiled, P, st, &f->last_kernel, &f->launches);
                 if (k_begin == -1) k_begin = unit_try_launch(f->unit, P, st, &f->last_kernel, &f->launches);
+                if (k_begin == -1) k_begin = decim_try_launch(f->decim, P, st, &f->last_kernel, &f->launches);
                 if (k_begin == -2) return fail(MRB_ERR_CUDA, "fast-path launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
             if (k_begin != 0) {            // generic kernel: everything, or the head the tiled kernel left out

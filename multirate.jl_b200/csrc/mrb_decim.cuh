@@ -1,0 +1,274 @@
+// mrb_decim.cuh -- fast path for FIRDecimator (src/Filters.jl:598-631) on complex64 samples x float32 taps
+// (BASELINE configs[1]: 1//8, 256 taps, 1024 channels, streamed 64K-sample chunks).
+//
+// y[k] = sum_i hflip[i] x[kM + i + e]: every output needs M new samples and T old ones, so a lane-per-channel
+// mapping would need > 2 KB of shared memory per lane.  Instead the filter is split into its M polyphase
+// residues: with i = jM + q,
+//     y[k] = sum_q  sum_j hflip[jM + q] * x_q[k + j],      x_q[m] = x[mM + q + e]
+// i.e. M unit-stride sub-filters of T/M taps over the decimated streams x_q.  One LANE is one (channel, residue)
+// pair: a warp covers 32/M channels, the taps of a lane are M-strided constants held in registers for the whole
+// kernel, each lane accumulates M consecutive partial outputs from a sliding register window (plain FFMA, full
+// FP32 rate), and a log2(M)-round shuffle reduce-scatter leaves output k0+q in residue lane q -- so a channel's M
+// results are written as one contiguous 8M-byte segment.  All 32 lanes of a warp do useful FMAs and a channel costs
+// 1/M-th of a warp's shared memory: 16 warps per SM fit.
+//  * rows of M samples per channel arrive by TMA ([32 ch][M samples] boxes, one per decimated index m) in a ring
+//    laid out [row][channel][M samples]: a warp's LDS.64 reads 256 contiguous bytes, conflict free.
+//  * one CTA barrier per step (M outputs per channel = 8 warps x ~600 instructions).
+// The first outputs of a chunk (window reaches into the history) are computed by k_generic.
+#pragma once
+#include <cstdio>
+
+#include "mrb_tiled.cuh"
+
+namespace mrb {
+
+constexpr int kDecRows = 32;            // channels per CTA
+constexpr int kDecTQ = 33;              // tap slots per residue: T <= 32 M, plus one slot of slack for alignment
+constexpr int kDecWarps = 8;
+
+struct alignas(16) DecParams {
+    long long k_begin, N;      // this launch covers outputs [k_begin, N)
+    long long e;               // x index of the first sample of output 0's (padded) window
+    int KT;                    // outputs per tile (multiple of M)
+    int delta;                 // which tap table: TMA box starts must be 16-byte aligned, i.e. on an even sample, so
+                               // the padded window starts at e (even) and the taps are placed delta slots later
+    float taps[2][32 * kDecTQ];   // taps[delta][q * kDecTQ + j] = padded hflip[j*M + q]
+};
+
+template <int M>
+struct DecCfg {
+    static constexpr int G = 8 / M;                                 // groups of M outputs per lane per step (R = 8)
+    static constexpr int R = G * M;                                 // outputs per channel per step
+    static constexpr int CPW = 32 / M;                              // channels per warp
+    static constexpr int WARPS = kDecRows / CPW;                    // warps per CTA (32 channels)
+    static constexpr int ROW_BYTES = kDecRows * M * 8;              // one decimated index, all channels
+    static constexpr int LIVE = R + kDecTQ - 1;                     // rows a step reads
+    static constexpr int LIVE_SLOTS = (LIVE + R - 1) / R;           // ... in units of R rows (one mbarrier each)
+    static constexpr int NSLOT = LIVE_SLOTS + 2;                    // ring: live + two steps ahead
+    static constexpr int NROW = NSLOT * R;
+    static constexpr int SMEM = NROW * ROW_BYTES + 8 * NSLOT;
+};
+
+template <int M>
+__global__ void __launch_bounds__(32 * DecCfg<M>::WARPS, M <= 8 ? 2 : 1)
+k_decim_c64(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, long long ldy, int nch,
+            const __grid_constant__ DecParams P) {
+    using C = DecCfg<M>;
+    constexpr int R = C::R, NSLOT = C::NSLOT;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + C::NROW * C::ROW_BYTES);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int q = lane & (M - 1);                                    // residue of this lane
+    const int cl = warp * C::CPW + lane / M;                         // channel within the CTA
+    const int ch0 = blockIdx.y * kDecRows;
+    const uint32_t in_base = smem_u32(smem), bar_base = smem_u32(bars);
+    const uint32_t lanepart = (uint32_t)(cl * M + q) * 8u;           // this lane's sample inside a row
+
+    const long long k0 = P.k_begin + (long long)blockIdx.x * P.KT;   // first output of the tile
+    const int ntile = (int)min((long long)P.KT, P.N - k0);
+    const int nsteps = (ntile + R - 1) / R;
+    const long long x0 = P.e + k0 * M;                               // x index of row 0 of the tile (even)
+    const int glast = nsteps + (C::LIVE - 1) / R;                    // newest row group (R rows) the tile reads
+
+    // this lane's taps: constants for the whole kernel
+    float t[kDecTQ];
+#pragma unroll
+    for (int j = 0; j < kDecTQ; ++j) t[j] = P.taps[P.delta][q * kDecTQ + j];
+
+    // one mbarrier per group of R rows; a group is R TMA boxes [32 ch][M samples]
+    auto issue_group = [&](int g, int slot) {
+        const uint32_t bar = bar_base + 8 * slot;
+        mbar_expect_tx(bar, R * C::ROW_BYTES);
+        for (int r = 0; r < R; ++r)
+            tma_load_2d(in_base + (uint32_t)((slot * R + r) * C::ROW_BYTES), &tmx,
+                        (int)((x0 + ((long long)g * R + r) * M) * 2), ch0, bar);
+    };
+    if (tid == 0) {
+        for (int i = 0; i < NSLOT; ++i) mbar_init(bar_base + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
+        for (int g = 0; g < NSLOT && g <= glast; ++g) issue_group(g, g);
+    }
+    __syncthreads();
+
+    int g_issued = min(NSLOT, glast + 1), i_slot = g_issued % NSLOT;
+    int g_waited = 0, w_slot = 0;
+    uint32_t w_par = 0;
+
+    for (int s = 0; s < nsteps; ++s) {
+        // rows [sR, sR + R + TQ - 1) of the tile = groups s .. s + (LIVE-1)/R
+        const int need = s + (C::LIVE - 1) / R;
+        for (; g_waited <= need; ++g_waited) {
+            mbar_wait(bar_base + 8 * w_slot, w_par);
+            if (++w_slot == NSLOT) { w_slot = 0; w_par ^= 1u; }
+        }
+        float2 w[C::LIVE];
+        {
+            int row = (s % NSLOT) * R;
+#pragma unroll
+            for (int m = 0; m < C::LIVE; ++m) {
+                const uint32_t a = in_base + (uint32_t)(row * C::ROW_BYTES) + lanepart;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w[m].x), "=f"(w[m].y) : "r"(a) : "memory");
+                if (++row == C::NROW) row = 0;
+            }
+        }
+        float2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kDecTQ; ++j) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                acc[r].x = fmaf(t[j], w[r + j].x, acc[r].x);
+                acc[r].y = fmaf(t[j], w[r + j].y, acc[r].y);
+            }
+        }
+        // ---- reduce-scatter over the M residue lanes, one group of M outputs at a time: afterwards lane q holds
+        // outputs sR + gM + q
+#pragma unroll
+        for (int g = 0; g < C::G; ++g) {
+#pragma unroll
+            for (int h = M / 2; h >= 1; h >>= 1) {
+                const bool up = (q & h) != 0;
+#pragma unroll
+                for (int i = 0; i < h; ++i) {
+                    const float2 keep = up ? acc[g * M + i + h] : acc[g * M + i];
+                    const float2 send = up ? acc[g * M + i] : acc[g * M + i + h];
+                    float2 got;
+                    got.x = __shfl_xor_sync(0xffffffffu, send.x, h);
+                    got.y = __shfl_xor_sync(0xffffffffu, send.y, h);
+                    acc[g * M + i] = make_float2(keep.x + got.x, keep.y + got.y);
+                }
+            }
+            const long long k = k0 + (long long)s * R + g * M + q;
+            const int c = ch0 + cl;
+            if (k < P.N && c < nch) y[(long long)c * ldy + k] = acc[g * M];
+        }
+
+        // ---- every warp is done with the rows before the next step's window: refill them
+        __syncthreads();
+        const int gtarget = min(s + 1 + NSLOT - 1, glast);
+        if (tid == 0) {
+            int sl = i_slot;
+            for (int g = g_issued; g <= gtarget; ++g) {
+                issue_group(g, sl);
+                if (++sl == NSLOT) sl = 0;
+            }
+        }
+        if (gtarget >= g_issued) {
+            i_slot = (i_slot + (gtarget + 1 - g_issued)) % NSLOT;
+            g_issued = gtarget + 1;
+        }
+    }
+    for (; g_waited < g_issued; ++g_waited) {             // every issued load must have landed before exit
+        mbar_wait(bar_base + 8 * w_slot, w_par);
+        if (++w_slot == NSLOT) { w_slot = 0; w_par ^= 1u; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+struct DecPlan {
+    bool ok = false;
+    int M = 8;
+    int64_t T = 0;
+    DecParams *hp = nullptr;
+    PFN_encodeTiled encode = nullptr;
+    int num_sms = 148;
+};
+
+static inline void decim_release(DecPlan &p) {
+    delete p.hp;
+    p.hp = nullptr;
+    p.ok = false;
+}
+
+// kind/tx/ty are the mrb.h enums (2 decimator ; 2 = complex64)
+static inline int32_t decim_prepare(DecPlan &p, int kind, int tx, int ty, int64_t L, int64_t M, int64_t T,
+                                    const std::vector<double> &bank, const cudaDeviceProp &prop) {
+    p.ok = false;
+    if (kind != 2 || tx != 2 || ty != 2 || L != 1) return 0;
+    if (!(M == 2 || M == 4 || M == 8) || T > (kDecTQ - 1) * M) return 0;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int32_t)(e ? e : cudaErrorUnknown);
+    p.encode = (PFN_encodeTiled)fn;
+    p.num_sms = prop.multiProcessorCount;
+    p.M = (int)M; p.T = T;
+    p.hp = new DecParams();
+    memset(p.hp, 0, sizeof(DecParams));
+    // padded taps: Tp = 33 M slots; zf zeros in front (they multiply samples older than the window), delta zeros
+    // behind (they multiply samples newer than x[n_k]: finite data or TMA zero fill)
+    const int64_t Tp = kDecTQ * M;
+    for (int64_t delta = 0; delta < 2; ++delta) {
+        const int64_t zf = Tp - T - delta;
+        for (int64_t i = 0; i < T; ++i) {
+            const int64_t ip = i + zf;
+            p.hp->taps[delta][(ip % M) * kDecTQ + ip / M] = (float)bank[i];   // bank = flipud(h): tap i multiplies window sample i
+        }
+    }
+    if (M == 4) e = cudaFuncSetAttribute(k_decim_c64<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<4>::SMEM);
+    else if (M == 8) e = cudaFuncSetAttribute(k_decim_c64<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<8>::SMEM);
+    else e = cudaFuncSetAttribute(k_decim_c64<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<2>::SMEM);
+    if (e != cudaSuccess) return (int32_t)e;
+    p.ok = true;
+    return 0;
+}
+
+// Launch for outputs [k_begin, N) of this chunk.  Returns k_begin (>= 0; the caller computes the outputs before it
+// with the generic kernel), -1 when the call is not covered, -2 on a CUDA error.
+static inline int64_t decim_try_launch(DecPlan &p, const GenParams &G, cudaStream_t st, const char **name,
+                                       int64_t *launches) {
+    static const bool trace = getenv("MRB_TRACE") != nullptr;
+#define MRB_DEC_SKIP(why) do { if (trace) fprintf(stderr, "[mrb] decimator kernel not used: %s\n", why); return -1; } while (0)
+    if (!p.ok) MRB_DEC_SKIP("configuration not covered");
+    if (G.mode != SEQ_INTEGER || G.L != 1 || G.p0 != 0) MRB_DEC_SKIP("not a decimator schedule");
+    if (((uintptr_t)G.x & 15) || ((uintptr_t)G.y & 7) || (G.ldx & 1)) MRB_DEC_SKIP("alignment");
+    if (G.n_in >= (1ll << 29) || G.nout >= (1ll << 29)) MRB_DEC_SKIP("size");
+    const int M = p.M;
+    const int64_t Tp = (int64_t)kDecTQ * M;
+    // output k reads x[kM + d0m1 - (T-1) .. kM + d0m1]; with zf = Tp - T - delta zeros in front the padded window
+    // starts at e = d0m1 - (T-1) - zf, and delta makes e even (16-byte aligned TMA box starts)
+    const int64_t e0 = G.d0m1 - (p.T - 1) - (Tp - p.T);
+    const int64_t delta = ((e0 % 2) + 2) % 2;
+    const int64_t e = e0 + delta;
+    int64_t k_begin = e >= 0 ? 0 : ceil_div(-e, M);
+    k_begin = (k_begin + M - 1) / M * M;
+    if (G.nout - k_begin < 64) MRB_DEC_SKIP("chunk too short");
+
+    DecParams &P = *p.hp;
+    P.k_begin = k_begin; P.N = G.nout; P.e = e; P.delta = (int)delta;
+    const int64_t span = G.nout - k_begin;
+    const int64_t groups = ceil_div(G.nch, kDecRows);
+    const int64_t R = 8;                                     // DecCfg<M>::R
+    int64_t tiles = std::max<int64_t>(1, std::min<int64_t>(span / (8 * R), ceil_div(4ll * 2 * p.num_sms, groups)));
+    P.KT = (int)(ceil_div(ceil_div(span, tiles), R) * R);
+    tiles = ceil_div(span, P.KT);
+
+    CUtensorMap tmx;
+    cuuint64_t dims[2] = {(cuuint64_t)(2 * G.n_in), (cuuint64_t)G.nch};
+    cuuint64_t strides[1] = {(cuuint64_t)G.ldx * 8};
+    cuuint32_t box[2] = {(cuuint32_t)(2 * M), kDecRows};
+    cuuint32_t es[2] = {1, 1};
+    if (p.encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(G.x), dims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        MRB_DEC_SKIP("x tensor map");
+#undef MRB_DEC_SKIP
+    dim3 grid((unsigned)tiles, (unsigned)groups);
+    float2 *yy = static_cast<float2 *>(G.y);
+    if (M == 4) k_decim_c64<4><<<grid, 32 * DecCfg<4>::WARPS, DecCfg<4>::SMEM, st>>>(tmx, yy, G.ldy, (int)G.nch, P);
+    else if (M == 8) k_decim_c64<8><<<grid, 32 * DecCfg<8>::WARPS, DecCfg<8>::SMEM, st>>>(tmx, yy, G.ldy, (int)G.nch, P);
+    else k_decim_c64<2><<<grid, 32 * DecCfg<2>::WARPS, DecCfg<2>::SMEM, st>>>(tmx, yy, G.ldy, (int)G.nch, P);
+    if (cudaPeekAtLastError() != cudaSuccess) return -2;
+    *name = M == 4 ? "decim_c64_m4" : M == 8 ? "decim_c64_m8" : "decim_c64_m2";
+    ++*launches;
+    return k_begin;
+}
+
+}  // namespace mrb

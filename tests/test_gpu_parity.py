@@ -309,3 +309,35 @@ def test_unit_stride_f32_kernel_shapes(L, ntaps, nch, rng):
         assert nerr(y[: min(nch, 3)], w) <= 1e-5
         assert nerr(yg.cpu().numpy(), y) <= 2e-6
     assert f.last_kernel.startswith("unit_f32"), f.last_kernel
+
+
+@pytest.mark.parametrize("M,ntaps,nch", [(8, 256, 33), (8, 100, 5), (8, 7, 64), (4, 128, 40), (4, 33, 1), (2, 64, 31),
+                                          (2, 19, 96)])
+def test_decimator_c64_kernel_shapes(M, ntaps, nch, rng):
+    """The complex64 decimator fast path (mrb_decim.cuh): ragged tap counts, ragged channel counts, chunk
+    lengths that leave every possible input deficit behind (so the window start takes every alignment), empty
+    outputs; count / state exact, values against the oracle and the generic kernel."""
+    import torch
+    h = rng.standard_normal(ntaps).astype(np.float32)
+    ratio = Fraction(1, M)
+    n = 9000
+    x = rand_samples(rng, (nch, n), np.complex64)
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, ratio)
+    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=np.complex64)
+    g.set_kernel_policy(1)
+    o = mo.FIRFilter(h, ratio)
+    edges = [0, 3000, 3001, 3003, 6000 + M // 2, 6000 + M // 2 + 2, n]
+    used = set()
+    for a, b in zip(edges[:-1], edges[1:]):
+        yd = f.filt(xd[:, a:b])
+        yg = g.filt(xd[:, a:b])
+        w = o.filt(x[: min(nch, 3), a:b])
+        torch.cuda.synchronize()
+        y = yd.cpu().numpy()
+        assert y.shape == (nch, w.shape[1])
+        assert nerr(y[: min(nch, 3)], w) <= 1e-5
+        assert nerr(yg.cpu().numpy(), y) <= 2e-6
+        assert states_equal(f, o)
+        used.add(f.last_kernel)
+    assert any(k.startswith("decim_c64") for k in used), used
