@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmrb.so")
 SOURCES = ["mrb_api.cu"]
-HEADERS = ["mrb_kernels.cuh", "mrb_tiled.cuh", "mrb_unit.cuh", "mrb_decim.cuh", "mrb_seq.h", os.path.join("..", "..", "include", "mrb.h")]
+HEADERS = ["mrb_kernels.cuh", "mrb_tiled.cuh", "mrb_unit.cuh", "mrb_decim.cuh", "mrb_table.cuh", "mrb_seq.h", os.path.join("..", "..", "include", "mrb.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC,-ffp-contract=off"]

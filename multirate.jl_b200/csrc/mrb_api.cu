@@ -18,6 +18,7 @@
 #include "mrb_tiled.cuh"
 #include "mrb_unit.cuh"
 #include "mrb_decim.cuh"
+#include "mrb_table.cuh"
 
 using namespace mrb;
 
@@ -86,9 +87,12 @@ struct mrb_filter {
     void *d_xs = nullptr, *d_ys = nullptr;
     size_t xs_bytes = 0, ys_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    // table kinds: the schedule of the call in flight, replayed once in check_filt_args and used by run_channels
+    std::vector<int64_t> vn; std::vector<int32_t> vphi; std::vector<double> va;
     TiledPlan tiled;                   // fast-path resources (mrb_tiled.cuh)
     UnitPlan unit;                     // fast path for float32 standard / interpolator (mrb_unit.cuh)
     DecPlan decim;                     // fast path for complex64 decimators (mrb_decim.cuh)
+    TabPlan table;                     // fast path for arbitrary / farrow on real samples (mrb_table.cuh)
     int policy = 0;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // one pair per timed mrb_filt
@@ -112,6 +116,7 @@ static void free_device(mrb_filter *f) {
     tiled_release(f->tiled);
     unit_release(f->unit);
     decim_release(f->decim);
+    table_release(f->table);
     for (auto &p : f->tev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (f->own_stream) cudaStreamDestroy(f->own_stream);
 }
@@ -228,6 +233,8 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
         if (rc != 0) return fail(MRB_ERR_CUDA, "unit_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
         rc = decim_prepare(f->decim, kind, f->tx, f->ty, f->L, f->M, f->T, f->bank, prop);
         if (rc != 0) return fail(MRB_ERR_CUDA, "decim_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
+        rc = table_prepare(f->table, kind, f->tx, f->ty, f->T, prop);
+        if (rc != 0) return fail(MRB_ERR_CUDA, "table_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
         CU(cudaDeviceSynchronize());
     }
     *out = f.release();
@@ -545,10 +552,9 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
         } else {
             int32_t rc = ensure_sched(f);
             if (rc) return rc;
-            // exact replay on the host (data independent), uploaded in bounded sub-chunks
-            std::vector<int64_t> vn; std::vector<int32_t> vphi; std::vector<double> va;
-            vn.reserve(N); va.reserve(N);
-            replay_table(f, n_in, nullptr, &vn, f->kind == MRB_ARBITRARY ? &vphi : nullptr, &va);
+            // the exact host replay (data independent) was done by check_filt_args; uploaded in bounded sub-chunks
+            const std::vector<int64_t> &vn = f->vn; const std::vector<int32_t> &vphi = f->vphi; const std::vector<double> &va = f->va;
+            if ((int64_t)vn.size() != N) return fail(MRB_ERR_BAD_ARGUMENT, "internal: schedule not prepared");
             int si = 0;
             for (int64_t k0 = 0; k0 < N; k0 += kSchedChunk, si ^= 1) {
                 const int64_t cnt = std::min(kSchedChunk, N - k0);
@@ -565,8 +571,23 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 CU(cudaEventRecord(s.ev, st));
                 s.pending = true;
                 P.sn = s.d_n; P.k_base = k0; P.nout = cnt;
+                P.sphi = s.d_phi; P.salpha = s.d_a;
+                if (f->policy == 0) {
+                    // fast path: per-output tap rows built once for all channels, then one dot product per output
+                    int64_t head = 0;                          // outputs of the slice whose window reaches the history
+                    while (head < cnt && vn[k0 + head] < f->H) ++head;
+                    const int64_t kb = table_try_launch(f->table, P, f->kind, f->polyorder + 1, f->th == MRB_F32, f->d_bank,
+                                                        f->d_dbank, f->d_pnfb, f->rate, k0, cnt, head, st, &f->last_kernel,
+                                                        &f->launches);
+                    if (kb == -2) return fail(MRB_ERR_CUDA, "table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    if (kb == 0) continue;
+                    if (kb > 0) P.nout = kb;                   // the generic kernel computes the slice's head
+                    else f->last_kernel = "generic";
+                } else {
+                    f->last_kernel = "generic";
+                }
                 if (f->kind == MRB_ARBITRARY) {
-                    P.mode = SEQ_ARBITRARY; P.sphi = s.d_phi; P.salpha = s.d_a;
+                    P.mode = SEQ_ARBITRARY;
                 } else {
                     P.mode = SEQ_FARROW; P.taptab = f->d_taptab;
                     const unsigned g = (unsigned)ceil_div(cnt * f->T, 256);
@@ -579,7 +600,6 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 dispatch_generic(f, P, st);
                 ++f->launches;
             }
-            f->last_kernel = "generic";
         }
     }
     if (t0) { CU(cudaEventRecord(t1, st)); f->tev.emplace_back(t0, t1); }
@@ -596,7 +616,12 @@ static int32_t check_filt_args(mrb_filter *f, const void *x, int64_t ldx, int64_
     if (!f) return fail(MRB_ERR_BAD_ARGUMENT, "null handle");
     if (f->device < 0) return fail(MRB_ERR_NO_DEVICE, "host-only handle: no CUDA device bound, and there is no CPU fallback");
     if (n_in < 0 || (n_in > 0 && !x) || ldx < n_in) return fail(MRB_ERR_BAD_ARGUMENT, "bad x / ld_x / n_in");
-    *N = count_outputs(f, n_in, end);
+    if (is_table_kind(f)) {
+        f->vn.clear(); f->vphi.clear(); f->va.clear();
+        *N = replay_table(f, n_in, end, &f->vn, f->kind == MRB_ARBITRARY ? &f->vphi : nullptr, &f->va);
+    } else {
+        *N = count_outputs(f, n_in, end);
+    }
     if (*N > cap) {
         const char *msg = f->kind == MRB_STANDARD ? "buffer length must be >= x length"                    // :460
                           : f->kind == MRB_INTERPOLATOR ? "length( buffer ) must be >= interpolation * length(x)"  // :503

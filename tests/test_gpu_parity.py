@@ -341,3 +341,37 @@ def test_decimator_c64_kernel_shapes(M, ntaps, nch, rng):
         assert states_equal(f, o)
         used.add(f.last_kernel)
     assert any(k.startswith("decim_c64") for k in used), used
+
+
+@pytest.mark.parametrize("tx", [np.float32, np.float64])
+@pytest.mark.parametrize("polyorder", [None, 4])
+@pytest.mark.parametrize("rate,nch", [(0.918734, 33), (1.37, 64), (1 / 2.123456789, 5)])
+def test_table_kernel_arbitrary_farrow(tx, polyorder, rate, nch, rng):
+    """The arbitrary / farrow fast path (mrb_table.cuh: tap rows built once per chunk, TMA ring, one dot product
+    per output): chunked streaming on the device against the oracle and the generic kernel; counts, phase
+    accumulator, alpha and deficit bit-exact after every chunk."""
+    import torch
+    N = 32
+    hLen, beta = mo.kaiserlength(0.05, samplerate=N)
+    hLen = -(-hLen // N) * N
+    h = (mo.firdes(hLen, 0.45, beta, samplerate=32) * N).astype(tx)          # test/runtests.jl:336-341
+    n = 12000
+    x = rand_samples(rng, (nch, n), tx)
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, rate, N, polyorder)
+    g = mr.FIRFilter(h, rate, N, polyorder, nchannels=nch, sample_dtype=tx)
+    g.set_kernel_policy(1)
+    o = mo.FIRFilter(h, rate, N, polyorder)
+    used = set()
+    for a, b in ((0, 5000), (5000, 5004), (5004, 9000), (9000, n)):
+        yd = f.filt(xd[:, a:b])
+        yg = g.filt(xd[:, a:b])
+        w = o.filt(x[:2, a:b])
+        torch.cuda.synchronize()
+        y = yd.cpu().numpy()
+        assert y.shape == (nch, w.shape[1])
+        assert nerr(y[:2], w) <= tol_for(tx), (a, b, nerr(y[:2], w))
+        assert nerr(yg.cpu().numpy(), y) <= (2e-6 if tx == np.float32 else 1e-13)
+        assert states_equal(f, o)
+        used.add(f.last_kernel)
+    assert any(k.startswith("table_") for k in used), used
