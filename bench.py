@@ -298,6 +298,19 @@ def main():
                 "frac": (achieved / peak) if achieved else None, "traffic": None,
                 "kernel": f.last_kernel, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": peak_src}
+    # FP32 side of the roofline: real FMAs the kernel executes per output and channel.  Only the 147//160
+    # shard (c5) is HBM-bound; decimator-256, standard-128 and the arbitrary-rate kernels sit on the FP32 roof.
+    taps_per_out = {"c5": 24, "c1": 24, "c2": 256, "c3a": 32, "c3b": 128, "c4a": 73, "c4f": 73}[w]
+    flops = 2 * taps_per_out * (2 if np.dtype(tx).kind == "c" else 1)
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                       # nominal, TFLOP/s
+    if kms:
+        tf = per_step_out * flops / (kms * 1e-3) / 1e12
+        roofline["fp32"] = {"flops_per_output": flops, "achieved_tflops": tf, "peak_tflops_nominal": fp32_peak,
+                            "frac": tf / fp32_peak,
+                            "note": "arbitrary: taps blended once per output (73 FMAs), the reference does two dot products"
+                                    if w == "c4a" else None}
+        if w in ("c2", "c3b", "c4a", "c4f"):
+            roofline["bound"] = "fp32 (see roofline.fp32; hbm fields kept for reference)"
     tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % w)
     if os.path.exists(tr):
         try:

@@ -101,14 +101,26 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     constexpr int OPW = kTabStep / kTabWarps;                        // outputs per warp per step
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *out_buf = smem + NB * BOX_BYTES;                  // [32 ch][32 outputs] R, 128-byte swizzle atoms
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(out_buf + kTabRows * kTabStep * sizeof(R));
+    // the tap rows and aligned window starts of a step (32 outputs), double buffered, fetched by bulk copies a
+    // step ahead: the taps are then read with warp-uniform LDS.128 instead of L2-latency global loads
+    const int row_bytes = kTabStep * P.rowlen * (int)sizeof(R);
+    unsigned char *rows_s = out_buf + kTabRows * kTabStep * sizeof(R);
+    int *ast_s = reinterpret_cast<int *>(rows_s + 2 * row_bytes);    // [2][32]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ast_s + 2 * kTabStep);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int ch0 = blockIdx.x * kTabRows;
     const uint32_t in_base = smem_u32(smem), obase = smem_u32(out_buf), bar_base = smem_u32(bars);
+    const uint32_t rbar_base = bar_base + 8 * NB;                    // two mbarriers for the staged rows
     const uint32_t rowpart = ((uint32_t)lane * 128u) ^ (((uint32_t)lane & 7u) << 4);   // SWIZZLE_128B
+    auto stage_rows = [&](long long kstep, int slot) {               // thread 0 only
+        const uint32_t bar = rbar_base + 8 * slot;
+        mbar_expect_tx(bar, (uint32_t)row_bytes + kTabStep * 4);
+        bulk_load(smem_u32(rows_s) + (uint32_t)(slot * row_bytes), rows + kstep * P.rowlen, (uint32_t)row_bytes, bar);
+        bulk_load(smem_u32(ast_s) + (uint32_t)(slot * kTabStep * 4), astart + kstep, kTabStep * 4, bar);
+    };
 
     const long long k0 = P.k_begin + (long long)blockIdx.y * P.KT;   // first output of the tile
     const int ntile = (int)min((long long)P.KT, P.N - k0);
@@ -119,10 +131,12 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 
     if (tid == 0) {
         if (in_base & 1023u) __trap();
-        for (int i = 0; i < NB; ++i) mbar_init(bar_base + 8 * i, 1);
+        for (int i = 0; i < NB + 2; ++i) mbar_init(bar_base + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmy) : "memory");
+        stage_rows(k0, 0);
+        if (nsteps > 1) stage_rows(k0 + kTabStep, 1);
         for (int jj = 0; jj < NB && jj <= jlast; ++jj) {
             mbar_expect_tx(bar_base + 8 * jj, BOX_BYTES);
             tma_load_2d(in_base + (uint32_t)(jj * BOX_BYTES), &tmx, xbase + jj * C::BOXE, ch0, bar_base + 8 * jj);
@@ -136,18 +150,22 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 
     for (int s = 0; s < nsteps; ++s) {
         const long long ks = k0 + (long long)s * kTabStep;
+        const int rslot = s & 1;
+        mbar_wait(rbar_base + 8 * rslot, (uint32_t)((s >> 1) & 1));  // this step's tap rows are in shared memory
+        const R *rows_step = reinterpret_cast<const R *>(rows_s + rslot * row_bytes);
+        const int *ast_step = ast_s + rslot * kTabStep;
 #pragma unroll 1
         for (int o = 0; o < OPW; ++o) {
             const long long k = ks + warp * OPW + o;
             R acc0 = R(0), acc1 = R(0), acc2 = R(0), acc3 = R(0);
             if (k <= klast) {
-                const int a0 = astart[k] - xbase;                    // tile-relative aligned window start (elements)
+                const int a0 = ast_step[warp * OPW + o] - xbase;     // tile-relative aligned window start (elements)
                 const int need = (a0 + P.rowlen - 1) / C::BOXE;
                 for (; j_waited <= need; ++j_waited) {
                     mbar_wait(bar_base + 8 * w_slot, w_par);
                     if (++w_slot == NB) { w_slot = 0; w_par ^= 1u; }
                 }
-                const R *row = rows + k * P.rowlen;
+                const R *row = rows_step + (warp * OPW + o) * P.rowlen;
                 for (int bb = 0; bb < P.nblk; ++bb) {
                     const int p = ((a0 + bb * TB) / A) % (8 * NB);   // ring position in 16-byte chunks
                     const unsigned *wt = P.win[p & 3] + (p & ~3);
@@ -173,13 +191,13 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
                         if constexpr (A == 4) {
-                            const float4 t = __ldg(reinterpret_cast<const float4 *>(tr) + q);
+                            const float4 t = reinterpret_cast<const float4 *>(tr)[q];
                             acc0 = fmaf(t.x, w[4 * q], acc0);
                             acc1 = fmaf(t.y, w[4 * q + 1], acc1);
                             acc2 = fmaf(t.z, w[4 * q + 2], acc2);
                             acc3 = fmaf(t.w, w[4 * q + 3], acc3);
                         } else {
-                            const double2 t = __ldg(reinterpret_cast<const double2 *>(tr) + q);
+                            const double2 t = reinterpret_cast<const double2 *>(tr)[q];
                             if (q & 1) { acc2 = fma(t.x, w[2 * q], acc2); acc3 = fma(t.y, w[2 * q + 1], acc3); }
                             else { acc0 = fma(t.x, w[2 * q], acc0); acc1 = fma(t.y, w[2 * q + 1], acc1); }
                         }
@@ -213,6 +231,8 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                 tma_load_2d(in_base + (uint32_t)(sl * BOX_BYTES), &tmx, xbase + jj * C::BOXE, ch0, bar);
                 if (++sl == NB) sl = 0;
             }
+            // the rows of step s+2 go where this step's rows were (every warp is past them: barrier above)
+            if (s + 2 < nsteps) stage_rows(ks + 2 * kTabStep, rslot);
             tma_wait_read<0>();                            // the staging buffer is rewritten in the next step
         }
         if (jtarget >= j_issued) {
@@ -251,14 +271,17 @@ static inline void table_release(TabPlan &p) {
 }
 
 template <typename R>
-static inline int table_smem() { return TabCfg<R>::NB * kTabRows * 128 + kTabRows * kTabStep * (int)sizeof(R) + 8 * TabCfg<R>::NB; }
+static inline int table_smem(int rowlen) {
+    return TabCfg<R>::NB * kTabRows * 128 + kTabRows * kTabStep * (int)sizeof(R) + 2 * kTabStep * rowlen * (int)sizeof(R) +
+           2 * kTabStep * 4 + 8 * (TabCfg<R>::NB + 2);
+}
 
 // kind/tx/ty are the mrb.h enums (4 arbitrary, 5 farrow ; 0 = float32, 1 = float64)
 static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_t T, const cudaDeviceProp &prop) {
     p.ok = false;
     if (!(kind == 4 || kind == 5)) return 0;
     if (!((tx == 0 && ty == 0) || (tx == 1 && ty == 1))) return 0;      // real samples, no promotion
-    if (T > 4 * 80 - 4) return 0;
+    if (T + 3 > 2 * (ty == 1 ? TabCfg<double>::TB : TabCfg<float>::TB)) return 0;   // two tap blocks: staged rows fit
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -279,8 +302,8 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
             const unsigned u = (unsigned)(c + i) % (unsigned)(8 * NB);
             p.hp->win[c][i] = ((u & 7u) << 4) | ((u >> 3) * (unsigned)(kTabRows * 128));
         }
-    e = p.dbl ? cudaFuncSetAttribute(k_table_fir<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, table_smem<double>())
-              : cudaFuncSetAttribute(k_table_fir<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, table_smem<float>());
+    e = p.dbl ? cudaFuncSetAttribute(k_table_fir<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, table_smem<double>(p.rowlen))
+              : cudaFuncSetAttribute(k_table_fir<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, table_smem<float>(p.rowlen));
     if (e != cudaSuccess) return (int32_t)e;
     p.ok = true;
     return 0;
@@ -290,9 +313,10 @@ static inline cudaError_t table_reserve(TabPlan &p, int64_t nout) {
     if (p.cap >= nout) return cudaSuccess;
     cudaFree(p.d_rows); cudaFree(p.d_astart);
     p.d_rows = nullptr; p.d_astart = nullptr; p.cap = 0;
-    cudaError_t e = cudaMalloc(&p.d_rows, (size_t)nout * p.rowlen * (p.dbl ? 8 : 4));
+    // two steps of slack: the kernel stages whole steps (32 rows) of the table
+    cudaError_t e = cudaMalloc(&p.d_rows, (size_t)(nout + 2 * kTabStep) * p.rowlen * (p.dbl ? 8 : 4));
     if (e != cudaSuccess) return e;
-    e = cudaMalloc(&p.d_astart, (size_t)nout * sizeof(int32_t));
+    e = cudaMalloc(&p.d_astart, (size_t)(nout + 2 * kTabStep) * sizeof(int32_t));
     if (e != cudaSuccess) return e;
     p.cap = nout;
     return cudaSuccess;
@@ -357,8 +381,8 @@ static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind,
         MRB_TAB_SKIP("y tensor map");
 #undef MRB_TAB_SKIP
     dim3 grid((unsigned)groups, (unsigned)tiles);
-    if (p.dbl) k_table_fir<double><<<grid, 128, table_smem<double>(), st>>>(tmx, tmy, (const double *)p.d_rows, p.d_astart, P);
-    else k_table_fir<float><<<grid, 128, table_smem<float>(), st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+    if (p.dbl) k_table_fir<double><<<grid, 128, table_smem<double>(p.rowlen), st>>>(tmx, tmy, (const double *)p.d_rows, p.d_astart, P);
+    else k_table_fir<float><<<grid, 128, table_smem<float>(p.rowlen), st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
     *name = p.dbl ? "table_f64" : "table_f32";
     ++*launches;
