@@ -154,16 +154,15 @@ __device__ __forceinline__ void load_window(unsigned long long (&xw)[2 * NP], co
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// RW outputs of one run (the first len-R0 are kept) from the register window.  R0 = first output of the run this
-// warp computes, DELTA = parity of the run's window start.
+// RW outputs of one run (the first `len` are kept) from the register window; j / kpos = bank row / tile-relative index
+// of the first output this warp computes, DELTA = parity of the run's window start.
 // ---------------------------------------------------------------------------------------------------------
-template <int TPAD, int RW, int R0, int DELTA, int OB>
+template <int TPAD, int RW, int DELTA, int OB>
 __device__ __forceinline__ void run_body(const TiledParams &P, const unsigned long long (&xw)[(TPAD + RW + 1) / 2 * 2],
                                          uint32_t rowpart, int j, int len, int kpos, uint32_t out_base) {
     static_assert(RW % OB == 0, "whole blocks");
-    const float4 *rows4 = P.bank + (j + R0) * (TPAD / 4);  // uniform base; everything below is base + constant
-    const int o0 = (kpos + R0) & 31;
-    len -= R0;
+    const float4 *rows4 = P.bank + j * (TPAD / 4);         // uniform base; everything below is base + constant
+    const int o0 = kpos & 31;
 #pragma unroll
     for (int rb = 0; rb < RW; rb += OB) {
         // One basic block per OB outputs (the uniform early exit below ends it): the rows of the bank are consumed
@@ -298,14 +297,12 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         }
         q_flushed = q_done;
 
+        // both halves run the same code (their windows were loaded RW samples apart): first row / output / count of
+        // this warp's part of the run are uniform values, not template parameters -- half the instruction footprint
         if (len > half * RW && !(P.dbg & 8)) {
-            if (half == 0) {
-                if (s & 1) run_body<TPAD, RW, 0, 1, OB>(P, xw, rowpart, j, len, k, out_base);
-                else run_body<TPAD, RW, 0, 0, OB>(P, xw, rowpart, j, len, k, out_base);
-            } else {
-                if (s & 1) run_body<TPAD, RW, RW, 1, OB>(P, xw, rowpart, j, len, k, out_base);
-                else run_body<TPAD, RW, RW, 0, OB>(P, xw, rowpart, j, len, k, out_base);
-            }
+            const int r0 = half * RW;
+            if (s & 1) run_body<TPAD, RW, 1, OB>(P, xw, rowpart, j + r0, len - r0, k + r0, out_base);
+            else run_body<TPAD, RW, 0, OB>(P, xw, rowpart, j + r0, len - r0, k + r0, out_base);
         }
 
         // ---- advance the (uniform) schedule by `len` outputs
