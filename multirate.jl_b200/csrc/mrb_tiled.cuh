@@ -228,10 +228,12 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 
     if (tid == 0) {
         if (in_base & 1023u) __trap();                               // the swizzle formulas assume 1 KiB alignment
+#pragma unroll 1
         for (int i = 0; i < NBOX; ++i) mbar_init(bar_base + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmy) : "memory");
+#pragma unroll 1
         for (int jj = 0; jj < NBOX; ++jj) {                          // prologue: fill the ring
             mbar_expect_tx(bar_base + 8 * jj, kBoxBytes);
             tma_load_2d(in_base + (uint32_t)(jj * kBoxBytes), &tmx, xc0 + jj * 16, ch0, bar_base + 8 * jj);
@@ -255,6 +257,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         const unsigned *wt = P.win[p & 3] + (p & ~3);
 
         // ---- this warp's window -> registers
+#pragma unroll 1
         for (; j_waited <= jneed; ++j_waited) {
             mbar_wait(bar_base + 8 * w_slot, w_par);
             if (++w_slot == NBOX) { w_slot = 0; w_par ^= 1u; }
@@ -274,6 +277,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         const int jtarget = min(max(jneed, min(jA_next + NBOX - 1, jend)), jA_next + NBOX - 1);
         if (tid == 0) {
             int sl = i_slot;
+#pragma unroll 1
             for (int jj = j_issued; jj <= jtarget; ++jj) {
                 const uint32_t bar = bar_base + 8 * sl;
                 mbar_expect_tx(bar, kBoxBytes);
@@ -285,6 +289,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
             // the start of chunk q_flushed, i.e. at most 4 chunks: with 4 buffers the two sets never share a
             // buffer, and everything older was confirmed by the wait above.
             if (flush && !(P.dbg & 4)) {
+#pragma unroll 1
                 for (int q = q_flushed; q < q_done; ++q) {
                     tma_store_2d(&tmy, yc0 + q * 16, ch0, out_base + (uint32_t)((q & (kOutBufs - 1)) * kOutBytes));
                     tma_commit();
@@ -312,6 +317,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     }
 
     // ---- drain: every issued load must have landed before the CTA gives its shared memory back
+#pragma unroll 1
     for (; j_waited < j_issued; ++j_waited) {
         mbar_wait(bar_base + 8 * w_slot, w_par);
         if (++w_slot == NBOX) { w_slot = 0; w_par ^= 1u; }
@@ -322,6 +328,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     __syncthreads();
     if (tid == 0) {
         const int q_end = (ntile + kOutChunk - 1) >> 3;
+#pragma unroll 1
         for (int q = q_flushed; q < q_end; ++q) {
             tma_store_2d(&tmy, yc0 + q * 16, ch0, out_base + (uint32_t)((q & (kOutBufs - 1)) * kOutBytes));
             tma_commit();
