@@ -52,6 +52,7 @@ constexpr int kBankFloats = 6000;       // tap bank capacity in kernel-parameter
 constexpr int kMaxTiles = 192;          // time tiles per launch (their start states ride in parameter space)
 constexpr int kMaxPhases = 1024;
 constexpr int kTPAD = 24, kRMAX = 12, kNBOX = 10;
+constexpr int kOB = 2;                  // outputs per basic block of the run body (1, 2 and 3 measure the same)
 constexpr int kRingPairs = 4 * kNBOX;   // sample pairs (16-byte chunks per row) the ring holds
 constexpr int kWinLen = (kRingPairs + (kTPAD + kRMAX) / 2 + 8 + 3) / 4 * 4;
 
@@ -352,7 +353,6 @@ struct TiledPlan {
     int T = 0;
     int kt_min = 1024;             // MRB_TILED_KT forces the time tile (tuning)
     bool kt_forced = false;
-    int ob = 3;                    // outputs per basic block (MRB_TILED_OB, tuning)
     int num_sms = 148;
     std::vector<int> row_of_phase;
 };
@@ -417,13 +417,8 @@ static inline int32_t tiled_prepare(TiledPlan &p, int kind, int tx, int ty, int6
         const int64_t wrap = (mp != 0 && len == to_wrap) ? 1 : 0;
         p.hp->runtab[j] = (int)(len | (wrap << 8) | (((j + len) % L) << 16));
     }
-    e = cudaFuncSetAttribute(k_tiled_c64<kTPAD, kRMAX, kNBOX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmem);
+    e = cudaFuncSetAttribute(k_tiled_c64<kTPAD, kRMAX, kNBOX, kOB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmem);
     if (e != cudaSuccess) return (int32_t)e;
-    e = cudaFuncSetAttribute(k_tiled_c64<kTPAD, kRMAX, kNBOX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmem);
-    if (e != cudaSuccess) return (int32_t)e;
-    e = cudaFuncSetAttribute(k_tiled_c64<kTPAD, kRMAX, kNBOX, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmem);
-    if (e != cudaSuccess) return (int32_t)e;
-    if (const char *ev = getenv("MRB_TILED_OB")) p.ob = atoi(ev);
     p.ok = true;
     return 0;
 }
@@ -492,9 +487,7 @@ static inline int64_t tiled_try_launch(TiledPlan &p, const GenParams &G, cudaStr
             return -1;
     }
     dim3 grid((unsigned)ntiles, (unsigned)ceil_div(G.nch, kTiledRows));
-    if (p.ob == 1) k_tiled_c64<kTPAD, kRMAX, kNBOX, 1><<<grid, kTiledThreads, kTiledSmem, st>>>(tmx, tmy, P);
-    else if (p.ob == 2) k_tiled_c64<kTPAD, kRMAX, kNBOX, 2><<<grid, kTiledThreads, kTiledSmem, st>>>(tmx, tmy, P);
-    else k_tiled_c64<kTPAD, kRMAX, kNBOX, 3><<<grid, kTiledThreads, kTiledSmem, st>>>(tmx, tmy, P);
+    k_tiled_c64<kTPAD, kRMAX, kNBOX, kOB><<<grid, kTiledThreads, kTiledSmem, st>>>(tmx, tmy, P);
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
     *name = "tiled_c64_t24_r12";
     ++*launches;
