@@ -48,7 +48,7 @@ struct UnitCfg {
 };
 
 template <int L, int R>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 4)
 k_unit_f32(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
            const __grid_constant__ UnitParams P) {
     using C = UnitCfg<L, R>;
@@ -251,7 +251,8 @@ static inline int64_t unit_try_launch(UnitPlan &p, const GenParams &G, cudaStrea
     const int64_t span = G.n_in - n_begin;
     // time tiles: whole steps, enough CTAs to fill the machine a few times over
     const int64_t groups = ceil_div(G.nch, kUnitRows);
-    int64_t tiles = std::max<int64_t>(1, std::min<int64_t>(span / (8 * IS), ceil_div(6ll * 3 * p.num_sms, groups)));
+    static const int wv = getenv("MRB_UNIT_WAVES") ? atoi(getenv("MRB_UNIT_WAVES")) : 12;
+    int64_t tiles = std::max<int64_t>(1, std::min<int64_t>(span / (8 * IS), ceil_div((int64_t)wv * 4 * p.num_sms, groups)));
     P.KT = (int)(ceil_div(ceil_div(span, tiles), IS) * IS);
     tiles = ceil_div(span, P.KT);
 
