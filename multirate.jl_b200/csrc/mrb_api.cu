@@ -669,7 +669,10 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
     // channel block: ~64 MiB of input per block, at least 1 channel
     int64_t cb = std::max<int64_t>(1, (int64_t)((64u << 20) / std::max<size_t>(1, (size_t)n_in * es)));
     cb = std::min(cb, f->nch);
-    const size_t xb = (size_t)cb * std::max<int64_t>(n_in, 1) * es, yb = (size_t)cb * std::max<int64_t>(N, 1) * eo;
+    // staging row pitches are multiples of 16 bytes, so the TMA fast paths apply whatever n_in and N are
+    const int64_t ax = std::max<int64_t>(1, 16 / (int64_t)es), ay = std::max<int64_t>(1, 16 / (int64_t)eo);
+    const int64_t lxs = (std::max<int64_t>(n_in, 1) + ax - 1) / ax * ax, lys = (std::max<int64_t>(N, 1) + ay - 1) / ay * ay;
+    const size_t xb = (size_t)cb * lxs * es, yb = (size_t)cb * lys * eo;
     rc = grow(&f->d_xs, &f->xs_bytes, 2 * xb); if (rc) return rc;
     rc = grow(&f->d_ys, &f->ys_bytes, 2 * yb); if (rc) return rc;
     static thread_local cudaStream_t s2 = nullptr;
@@ -681,12 +684,12 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
         char *dx = static_cast<char *>(f->d_xs) + b * xb, *dy = static_cast<char *>(f->d_ys) + b * yb;
         cudaStream_t st = sts[b];
         if (n_in > 0)
-            CU(cudaMemcpy2DAsync(dx, (size_t)n_in * es, static_cast<const char *>(x) + (size_t)(c0 * ldx) * es,
+            CU(cudaMemcpy2DAsync(dx, (size_t)lxs * es, static_cast<const char *>(x) + (size_t)(c0 * ldx) * es,
                                  (size_t)ldx * es, (size_t)n_in * es, (size_t)nc, cudaMemcpyHostToDevice, st));
-        rc = run_channels(f, dx, n_in, n_in, dy, std::max<int64_t>(N, 1), N, c0, nc, st);
+        rc = run_channels(f, dx, lxs, n_in, dy, lys, N, c0, nc, st);
         if (rc) return rc;
         if (N > 0)
-            CU(cudaMemcpy2DAsync(static_cast<char *>(y) + (size_t)(c0 * ldy) * eo, (size_t)ldy * eo, dy, (size_t)N * eo,
+            CU(cudaMemcpy2DAsync(static_cast<char *>(y) + (size_t)(c0 * ldy) * eo, (size_t)ldy * eo, dy, (size_t)lys * eo,
                                  (size_t)N * eo, (size_t)nc, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(sts[0]));

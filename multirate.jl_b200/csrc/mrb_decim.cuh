@@ -246,7 +246,8 @@ static inline int64_t decim_try_launch(DecPlan &p, const GenParams &G, cudaStrea
     const int64_t span = G.nout - k_begin;
     const int64_t groups = ceil_div(G.nch, kDecRows);
     const int64_t R = 8;                                     // DecCfg<M>::R
-    int64_t tiles = std::max<int64_t>(1, std::min<int64_t>(span / (8 * R), ceil_div(4ll * 2 * p.num_sms, groups)));
+    static const int wv = getenv("MRB_DEC_WAVES") ? atoi(getenv("MRB_DEC_WAVES")) : 4;
+    int64_t tiles = std::max<int64_t>(1, std::min<int64_t>(span / (8 * R), ceil_div((int64_t)wv * 2 * p.num_sms, groups)));
     P.KT = (int)(ceil_div(ceil_div(span, tiles), R) * R);
     tiles = ceil_div(span, P.KT);
 

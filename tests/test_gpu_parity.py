@@ -375,3 +375,27 @@ def test_table_kernel_arbitrary_farrow(tx, polyorder, rate, nch, rng):
         assert states_equal(f, o)
         used.add(f.last_kernel)
     assert any(k.startswith("table_") for k in used), used
+
+
+@pytest.mark.parametrize("case", ["rational", "decimator", "interpolator", "standard", "arbitrary", "farrow"])
+def test_host_path_uses_fast_kernels_for_any_length(case, rng):
+    """mrb_filt_host stages host buffers with 16-byte row pitches, so odd chunk lengths (and odd output counts)
+    still run the TMA fast paths; values against the oracle."""
+    N = 32
+    hl, beta = mo.kaiserlength(0.05, samplerate=N)
+    ha = (mo.firdes(-(-hl // N) * N, 0.45, beta, samplerate=32) * N).astype(np.float32)
+    cfg = {"rational": (Fraction(147, 160), mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32), np.complex64, "tiled"),
+           "decimator": (Fraction(1, 8), mo.firdes(256, 0.5 / 8, 7.8562).astype(np.float32), np.complex64, "decim"),
+           "interpolator": (Fraction(4, 1), mo.firdes(128, 0.5 / 4, 7.8562).astype(np.float32), np.float32, "unit"),
+           "standard": (Fraction(1, 1), mo.firdes(128, 0.25, 7.8562).astype(np.float32), np.float32, "unit"),
+           "arbitrary": (0.918734, ha, np.float32, "table"), "farrow": (0.918734, ha, np.float32, "table")}[case]
+    ratio, h, tx, want = cfg
+    extra = (N, 4) if case == "farrow" else (N,) if case == "arbitrary" else ()
+    x = rand_samples(rng, (37, 7001), tx)
+    f, o = mr.FIRFilter(h, ratio, *extra), mo.FIRFilter(h, ratio, *extra)
+    for a, b in ((0, 3001), (3001, 7001)):
+        y, w = f.filt(x[:, a:b]), o.filt(x[:3, a:b])
+        assert y.shape == (37, w.shape[1])
+        assert nerr(y[:3], w) <= 1e-5
+        assert f.last_kernel.startswith(want), (case, f.last_kernel)
+        assert states_equal(f, o)
