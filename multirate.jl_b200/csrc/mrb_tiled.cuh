@@ -270,12 +270,15 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         // before the NEXT run's window are free and are refilled now, a whole run ahead of their first use; (b) every
         // warp has staged the previous run's outputs, so completed chunks can leave.
         const int s_next = s + len + ((rt >> 8) & 1);          // the run ended on a phase wrap: the index skips one
-        const int jA_next = (k + len < ntile ? s_next : s) >> 3;
+        const bool has_next = k + len < ntile;
+        const int jA_next = (has_next ? s_next : s) >> 3;
+        // the next run's windows must be on their way after this barrier whatever the estimate `jend` says
+        const int jneed_next = has_next ? ((s_next & ~1) + 2 * NPRUN - 1) >> 3 : jneed;
         const bool flush = q_done > q_flushed;
         if (flush) fence_async_smem();                         // this thread's st.shared -> visible to the async proxy
         if (tid == 0) tma_wait_read<0>();                      // stores issued a run ago have left their buffers
         __syncthreads();
-        const int jtarget = min(max(jneed, min(jA_next + NBOX - 1, jend)), jA_next + NBOX - 1);
+        const int jtarget = min(max(jneed_next, min(jA_next + NBOX - 1, jend)), jA_next + NBOX - 1);
         if (tid == 0) {
             int sl = i_slot;
 #pragma unroll 1
