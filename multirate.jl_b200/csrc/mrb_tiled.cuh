@@ -1,5 +1,6 @@
 // mrb_tiled.cuh -- the tiled fast path for integer-schedule kernels with unit input stride
-// (FIRStandard, and FIRRational with L <= M < 2L such as 147//160), complex64 samples x float32 taps.
+// (FIRStandard, and FIRRational with L <= M < 2L such as 147//160 or M < L <= 1.5 M such as 160//147), complex64
+// samples x float32 taps.
 //
 // What the hardware measurements forced (tools/ubench*.cu, profiles/README.md):
 //  * lane = channel.  Every thread of a CTA walks the SAME outputs, so the phase / input-index bookkeeping of
@@ -67,8 +68,8 @@ struct alignas(16) TiledParams {
     //   s   : x-sample index of its window start, relative to box 0 of the tile
     //   xc0 : float coordinate of box 0 in the x tensor map
     struct Tile { int j, s, xc0, pad; } tile[kMaxTiles];
-    // per bank row j: run length (bits 0-7, <= RMAX), "run ends on a phase wrap" (bit 8: the input index then
-    // skips one extra sample), row of the next run's first output (bits 16-31)
+    // per bank row j: run length (bits 0-7, <= RMAX), "run ends on a phase wrap" (bit 8, M > L: the input index then
+    // skips one extra sample; bit 9, M < L: it repeats one), row of the next run's first output (bits 16-31)
     int runtab[kMaxPhases];
     // win[c][i] = W((c + i) mod kRingPairs): W(u) = swizzle chunk bits | ring slot offset of sample pair u.  Four
     // copies shifted by c = 0..3 so that a window starting at any pair is fetched with aligned 128-bit LDCU.
@@ -269,7 +270,8 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         // ---- the one barrier of the run.  Behind it (a) every warp holds its window in registers, so all boxes
         // before the NEXT run's window are free and are refilled now, a whole run ahead of their first use; (b) every
         // warp has staged the previous run's outputs, so completed chunks can leave.
-        const int s_next = s + len + ((rt >> 8) & 1);          // the run ended on a phase wrap: the index skips one
+        // the run ended on a phase wrap: the input index then skips one sample (M > L) or repeats one (M < L)
+        const int s_next = s + len + ((rt >> 8) & 1) - ((rt >> 9) & 1);
         const bool has_next = k + len < ntile;
         const int jA_next = (has_next ? s_next : s) >> 3;
         // the next run's windows must be on their way after this barrier whatever the estimate `jend` says
@@ -377,7 +379,10 @@ static inline int32_t tiled_prepare(TiledPlan &p, int kind, int tx, int ty, int6
     p.num_sms = prop.multiProcessorCount;
     const bool kind_ok = kind == 0 /*standard*/ || kind == 3 /*rational*/;
     if (!kind_ok || tx != 2 || ty != 2) return 0;
-    if (!(L <= M && M < 2 * L) || L > kMaxPhases || T > kTPAD || (L + kRMAX) * kTPAD > kBankFloats) return 0;
+    // unit input stride between consecutive outputs except at phase wraps: M in [L, 2L), or M < L with runs that are
+    // not too short on average (L / (L - M) >= 3 outputs)
+    const bool ratio_ok = (L <= M && M < 2 * L) || (M < L && 3 * (L - M) <= L);
+    if (!ratio_ok || L > kMaxPhases || T > kTPAD || (L + kRMAX) * kTPAD > kBankFloats) return 0;
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -399,11 +404,11 @@ static inline int32_t tiled_prepare(TiledPlan &p, int kind, int tx, int ty, int6
         const unsigned kk = (unsigned)i & 31u;
         p.hp->wout[i] = (((kk >> 1) & 3u) << 4) | ((kk & 1u) << 3) | (((kk >> 3) & 3u) * (unsigned)kOutBytes);
     }
-    const int64_t mp = M - L;                                          // phase step per output
+    const int64_t mp = M - L;                                          // phase step per output (mod L); < 0 when M < L
     p.row_of_phase.assign((size_t)L, 0);
     std::vector<int64_t> phase_of_row((size_t)L);
     for (int64_t j = 0; j < L; ++j) {
-        phase_of_row[j] = (j * mp) % L;                                // a bijection: gcd(M-L, L) == gcd(M, L) == 1
+        phase_of_row[j] = (j * M) % L;                                 // a bijection: gcd(M, L) == 1
         p.row_of_phase[phase_of_row[j]] = (int)j;
     }
     float *hb = reinterpret_cast<float *>(p.hp->bank);
@@ -414,10 +419,12 @@ static inline int32_t tiled_prepare(TiledPlan &p, int kind, int tx, int ty, int6
     }
     for (int64_t j = 0; j < L; ++j) {
         const int64_t ph = phase_of_row[j];
-        // outputs at phases ph, ph+mp, ... read consecutive input windows until the phase wraps past L
-        const int64_t to_wrap = mp == 0 ? kRMAX : (L - 1 - ph) / mp + 1;
+        // M >= L: outputs at phases ph, ph+mp, ... read consecutive input windows until the phase wraps past L (the
+        // input index then advances by two).  M < L: phases ph, ph-|mp|, ... until the phase drops below |mp| (the
+        // next output then reads the same window again).
+        const int64_t to_wrap = mp == 0 ? kRMAX : mp > 0 ? (L - 1 - ph) / mp + 1 : ph / (-mp) + 1;
         const int64_t len = std::min<int64_t>(to_wrap, kRMAX);
-        const int64_t wrap = (mp != 0 && len == to_wrap) ? 1 : 0;
+        const int64_t wrap = (mp != 0 && len == to_wrap) ? (mp > 0 ? 1 : 2) : 0;
         p.hp->runtab[j] = (int)(len | (wrap << 8) | (((j + len) % L) << 16));
     }
     e = cudaFuncSetAttribute(k_tiled_c64<kTPAD, kRMAX, kNBOX, kOB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmem);

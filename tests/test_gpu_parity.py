@@ -416,6 +416,13 @@ def test_fast_paths_random_stress_against_generic_kernel(rng):
             M = int(r.integers(L, 2 * L))
         cases.append((Fraction(L, M), int(r.integers(1, 24 * L + 1)), np.complex64, "tiled"))
     cases.append((Fraction(1, 1), 24, np.complex64, "tiled"))
+    cases.append((Fraction(160, 147), 24 * 160, np.complex64, "tiled"))         # interpolating rationals: M < L <= 1.5 M
+    for _ in range(8):
+        M = int(r.integers(2, 150))
+        L = int(r.integers(M + 1, M + M // 2 + 2))
+        while math.gcd(L, M) != 1 or 3 * (L - M) > L:
+            L = int(r.integers(M + 1, M + M // 2 + 2))
+        cases.append((Fraction(L, M), int(r.integers(1, 24 * L + 1)), np.complex64, "tiled"))
     for _ in range(4):                                             # unit: float32, L in {1, 2, 4}
         L = int(r.choice([1, 2, 4]))
         cases.append((Fraction(L, 1), int(r.integers(1, 128 * L + 1)), np.float32, "unit"))
