@@ -666,20 +666,26 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
     if (rc) return rc;
     CU(cudaSetDevice(f->device));
     const size_t es = dsize(f->tx), eo = dsize(f->ty);
-    // channel block: ~64 MiB of input per block, at least 1 channel
-    int64_t cb = std::max<int64_t>(1, (int64_t)((64u << 20) / std::max<size_t>(1, (size_t)n_in * es)));
+    // channel blocks of ~MRB_HOST_BLOCK_MIB (64) MiB of input, pipelined over MRB_HOST_STREAMS (1..4, default 2) streams
+    // (measured: 16..256 MiB x 2..4 streams all land on the same 86 GB/s full-duplex PCIe limit)
+    static const int blk_mib = getenv("MRB_HOST_BLOCK_MIB") ? std::max(1, atoi(getenv("MRB_HOST_BLOCK_MIB"))) : 64;
+    static const int nst = getenv("MRB_HOST_STREAMS") ? std::min(4, std::max(1, atoi(getenv("MRB_HOST_STREAMS")))) : 2;
+    int64_t cb = std::max<int64_t>(1, (int64_t)(((size_t)blk_mib << 20) / std::max<size_t>(1, (size_t)n_in * es)));
     cb = std::min(cb, f->nch);
     // staging row pitches are multiples of 16 bytes, so the TMA fast paths apply whatever n_in and N are
     const int64_t ax = std::max<int64_t>(1, 16 / (int64_t)es), ay = std::max<int64_t>(1, 16 / (int64_t)eo);
     const int64_t lxs = (std::max<int64_t>(n_in, 1) + ax - 1) / ax * ax, lys = (std::max<int64_t>(N, 1) + ay - 1) / ay * ay;
     const size_t xb = (size_t)cb * lxs * es, yb = (size_t)cb * lys * eo;
-    rc = grow(&f->d_xs, &f->xs_bytes, 2 * xb); if (rc) return rc;
-    rc = grow(&f->d_ys, &f->ys_bytes, 2 * yb); if (rc) return rc;
-    static thread_local cudaStream_t s2 = nullptr;
-    if (!s2) CU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-    cudaStream_t sts[2] = {f->own_stream, s2};
+    rc = grow(&f->d_xs, &f->xs_bytes, nst * xb); if (rc) return rc;
+    rc = grow(&f->d_ys, &f->ys_bytes, nst * yb); if (rc) return rc;
+    static thread_local cudaStream_t extra[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t sts[4] = {f->own_stream, nullptr, nullptr, nullptr};
+    for (int i = 1; i < nst; ++i) {
+        if (!extra[i - 1]) CU(cudaStreamCreateWithFlags(&extra[i - 1], cudaStreamNonBlocking));
+        sts[i] = extra[i - 1];
+    }
     int b = 0;
-    for (int64_t c0 = 0; c0 < f->nch; c0 += cb, b ^= 1) {
+    for (int64_t c0 = 0; c0 < f->nch; c0 += cb, b = (b + 1) % nst) {
         const int64_t nc = std::min(cb, f->nch - c0);
         char *dx = static_cast<char *>(f->d_xs) + b * xb, *dy = static_cast<char *>(f->d_ys) + b * yb;
         cudaStream_t st = sts[b];
@@ -692,8 +698,7 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
             CU(cudaMemcpy2DAsync(static_cast<char *>(y) + (size_t)(c0 * ldy) * eo, (size_t)ldy * eo, dy, (size_t)lys * eo,
                                  (size_t)N * eo, (size_t)nc, cudaMemcpyDeviceToHost, st));
     }
-    CU(cudaStreamSynchronize(sts[0]));
-    CU(cudaStreamSynchronize(sts[1]));
+    for (int i = 0; i < nst; ++i) CU(cudaStreamSynchronize(sts[i]));
     commit_state(f, end);
     if (n_in > 0 && f->H > 0) f->cur ^= 1;
     if (n_out) *n_out = N;

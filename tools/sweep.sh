@@ -1,27 +1,8 @@
 mkdir -p gpurun_out
-out=gpurun_out/s4_sweep23.txt; : > $out
-timeout 800 python -m pytest tests -m gpu -x -q --timeout 300 2>&1 | tail -12 >> $out
-python - >> $out 2>&1 <<'PY'
-import sys, time
-sys.path.insert(0, '.'); sys.path.insert(0, 'oracle')
-import numpy as np, torch
-from fractions import Fraction
-import multirate_b200 as mr, multirate_oracle as mo
-# the mirror of the headline: 160//147 (44.1k -> 48k), 8192 ch complex64
-h = mo.firdes(24 * 160, 0.5 / 160, 7.8562).astype(np.float32) * 160
-nch, n = 8192, 1 << 16
-x = torch.view_as_complex(torch.rand((nch, n, 2), device='cuda'))
-f = mr.FIRFilter(h, Fraction(160, 147), nchannels=nch, sample_dtype=np.complex64)
-N = f.outputlength(n); ybuf = torch.empty((nch, (N + 3) // 4 * 4), dtype=x.dtype, device='cuda')
-for _ in range(3): f.filt_(ybuf, x)
-torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-e0.record(); cnt = 0
-for _ in range(10): cnt += f._exact_count(n); f.filt_(ybuf, x)
-e1.record(); torch.cuda.synchronize(); ms = e0.elapsed_time(e1) / 10
-outs = cnt / 10 * nch
-print('160//147 x 8192 ch c64:', f.last_kernel, '%.3f ms/step' % ms, '%.1f Gout/s' % (outs / ms / 1e6), 'HBM frac %.3f' % ((nch * n * 8 + outs * 8) / (ms * 1e-3) / 6548.5e9))
-w = mo.filt(h, x[:2, :20000].cpu().numpy(), Fraction(160, 147))
-y = mr.FIRFilter(h, Fraction(160, 147)).filt(x[:2, :20000].contiguous()).cpu().numpy()
-print('parity vs oracle', float(np.abs(y - w).max() / np.abs(w).max()), y.shape == w.shape)
-PY
+out=gpurun_out/s4_sweep24.txt; : > $out
+for cfg in "64 2" "64 3" "32 3" "128 3" "32 4" "16 4" "256 2"; do
+  set -- $cfg
+  echo "block_mib=$1 streams=$2" >> $out
+  MRB_HOST_BLOCK_MIB=$1 MRB_HOST_STREAMS=$2 timeout 200 python bench.py --no-cpu --steps 3 --warmup 3 2>>$out | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['e2e']['value'], d['e2e']['ms_per_step'])" >> $out
+done
 cat $out
