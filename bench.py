@@ -202,6 +202,30 @@ def dtype_name(w):
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local):
+    """Pin this rank's host threads (and therefore its first-touch pinned staging buffers) to the NUMA node its GPU
+    hangs off: with one rank per GPU the end-to-end path otherwise funnels every rank's PCIe traffic through one
+    socket's memory.  Best effort; returns the node or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,6 +249,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -345,12 +370,12 @@ def main():
             dt, eo = a[0].item(), b[1].item()
         e2e = {"value": eo / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": nch * n * es,
                "d2h_bytes_per_step": int(per_step_out * es), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
-               "api": "FIRFilter.filt_(numpy pinned) -> mrb_filt_host"}
+               "api": "FIRFilter.filt_(numpy pinned) -> mrb_filt_host", "numa_node": numa}
         del xh_t, yh_t
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:                 # the CPU baseline is timed at N = 1 only
             try:
                 cpu = cpu_port_run(w, 3, 1)
                 cpu.pop("ms_per_step", None)
