@@ -22,7 +22,7 @@
 
 namespace mrb {
 
-constexpr int kDecRows = 32;            // channels per CTA
+constexpr int kDecRows = 32;            // channels per CTA (16-channel CTAs, 4 per SM, measured 6 % slower)
 constexpr int kDecTQ = 33;              // tap slots per residue: T <= 32 M, plus one slot of slack for alignment
 constexpr int kDecWarps = 8;
 
@@ -32,7 +32,8 @@ struct alignas(16) DecParams {
     int KT;                    // outputs per tile (multiple of M)
     int delta;                 // which tap table: TMA box starts must be 16-byte aligned, i.e. on an even sample, so
                                // the padded window starts at e (even) and the taps are placed delta slots later
-    float taps[2][32 * kDecTQ];   // taps[delta][q * kDecTQ + j] = padded hflip[j*M + q]
+    const float *taps;         // device: taps[delta][j * 32 + q] = padded hflip[j*M + q] (tap-major: a warp's loads of
+                               // one slot touch M consecutive floats)
 };
 
 template <int M>
@@ -50,7 +51,7 @@ struct DecCfg {
 };
 
 template <int M>
-__global__ void __launch_bounds__(32 * DecCfg<M>::WARPS, M <= 8 ? 2 : 1)
+__global__ void __launch_bounds__(32 * DecCfg<M>::WARPS, 2)
 k_decim_c64(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, long long ldy, int nch,
             const __grid_constant__ DecParams P) {
     using C = DecCfg<M>;
@@ -76,7 +77,7 @@ k_decim_c64(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, lon
     // this lane's taps: constants for the whole kernel
     float t[kDecTQ];
 #pragma unroll
-    for (int j = 0; j < kDecTQ; ++j) t[j] = P.taps[P.delta][q * kDecTQ + j];
+    for (int j = 0; j < kDecTQ; ++j) t[j] = __ldg(P.taps + (P.delta * kDecTQ + j) * 32 + q);
 
     // one mbarrier per group of R rows; a group is R TMA boxes [32 ch][M samples]
     auto issue_group = [&](int g, int slot) {
@@ -177,6 +178,7 @@ struct DecPlan {
     int M = 8;
     int64_t T = 0;
     DecParams *hp = nullptr;
+    float *d_taps = nullptr;
     PFN_encodeTiled encode = nullptr;
     int num_sms = 148;
 };
@@ -184,6 +186,8 @@ struct DecPlan {
 static inline void decim_release(DecPlan &p) {
     delete p.hp;
     p.hp = nullptr;
+    cudaFree(p.d_taps);
+    p.d_taps = nullptr;
     p.ok = false;
 }
 
@@ -205,13 +209,19 @@ static inline int32_t decim_prepare(DecPlan &p, int kind, int tx, int ty, int64_
     // padded taps: Tp = 33 M slots; zf zeros in front (they multiply samples older than the window), delta zeros
     // behind (they multiply samples newer than x[n_k]: finite data or TMA zero fill)
     const int64_t Tp = kDecTQ * M;
+    std::vector<float> ht((size_t)2 * kDecTQ * 32, 0.f);
     for (int64_t delta = 0; delta < 2; ++delta) {
         const int64_t zf = Tp - T - delta;
         for (int64_t i = 0; i < T; ++i) {
             const int64_t ip = i + zf;
-            p.hp->taps[delta][(ip % M) * kDecTQ + ip / M] = (float)bank[i];   // bank = flipud(h): tap i multiplies window sample i
+            ht[(size_t)((delta * kDecTQ + ip / M) * 32 + ip % M)] = (float)bank[i];   // bank = flipud(h): tap i multiplies window sample i
         }
     }
+    e = cudaMalloc(&p.d_taps, ht.size() * sizeof(float));
+    if (e != cudaSuccess) return (int32_t)e;
+    e = cudaMemcpy(p.d_taps, ht.data(), ht.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int32_t)e;
+    p.hp->taps = p.d_taps;
     if (M == 4) e = cudaFuncSetAttribute(k_decim_c64<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<4>::SMEM);
     else if (M == 8) e = cudaFuncSetAttribute(k_decim_c64<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<8>::SMEM);
     else e = cudaFuncSetAttribute(k_decim_c64<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<2>::SMEM);
