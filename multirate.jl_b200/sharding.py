@@ -38,3 +38,60 @@ def segment_plan(filt, n_samples: int, world: int, align: int = 1):
         _ffi.check(_ffi.lib().mrb_output_count(probe._handle, n1 - n0, C.byref(cnt)))
         plan.append((n0, n1, k0.value, cnt.value))
     return plan
+
+
+def filt_long_stream(h, ratio, x, rows_target: int = 8192):
+    """One very long single-channel stream at multichannel speed, with no copy and no collective (SURVEY 8e,
+    BASELINE configs[4] "one 2^31-sample stream split into segments with tap-length halo").
+
+    The stream is viewed in place as a channel-major matrix of `rows` segments of `seg` samples, seg a multiple of the
+    decimation M: every segment then starts from the constructor state (phase 0, deficit 1; src/Filters.jl:567-571
+    in closed form), its history is simply the H samples that precede it in memory (the halo), and it produces exactly
+    seg*L/M outputs, so the output matrix is the output stream, in place.  The tail that does not fill a segment runs
+    through a one-channel filter seeked to its position.  x: 1-D CUDA tensor (torch); returns the 1-D output tensor.
+    """
+    import math
+    from fractions import Fraction
+
+    import numpy as np
+    import torch
+
+    from .filters import FIRFilter
+    ratio = Fraction(ratio)
+    L, M = ratio.numerator, ratio.denominator
+    n = x.shape[0]
+    tx = np.dtype(str(x.dtype).replace("torch.", ""))
+    probe = FIRFilter(h, ratio, nchannels=1, sample_dtype=tx, device=-1)
+    H = probe.historyLen
+    # segment length: a multiple of M whose input and output row pitches are multiples of 16 bytes
+    al = max(1, 16 // tx.itemsize)
+    unit = M * al // math.gcd(M, al)
+    while (unit * L // M) % al:
+        unit *= 2
+    seg = max(unit, -(-(-(-n // max(rows_target, 1))) // unit) * unit)       # ceil: at most rows_target segments
+    rows = n // seg
+    seg_out = seg * L // M
+    total = probe._exact_count(n)
+    y = torch.empty(total, dtype=x.dtype, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    lib = _ffi.lib()
+    done_in = done_out = 0
+    if rows >= 2 and seg > 4 * H:
+        body = x[:rows * seg].view(rows, seg)
+        f = FIRFilter(h, ratio, nchannels=rows, sample_dtype=tx, device=x.device.index or 0)
+        halo = torch.zeros((rows, max(H, 1)), dtype=x.dtype, device=x.device)
+        if H:
+            idx = (torch.arange(1, rows, device=x.device) * seg).unsqueeze(1) + torch.arange(-H, 0, device=x.device)
+            halo[1:, :H] = x[idx]
+        k0 = C.c_int64()
+        _ffi.check(lib.mrb_seek(f._handle, 0, halo.data_ptr() if H else None, max(H, 1), C.byref(k0), stream))
+        f.filt_(y[:rows * seg_out].view(rows, seg_out), body)
+        done_in, done_out = rows * seg, rows * seg_out
+    if done_in < n:
+        g = FIRFilter(h, ratio, nchannels=1, sample_dtype=tx, device=x.device.index or 0)
+        k0 = C.c_int64()
+        halo = x[done_in - H:done_in].contiguous() if (done_in and H) else None
+        _ffi.check(lib.mrb_seek(g._handle, done_in, halo.data_ptr() if halo is not None else None, H, C.byref(k0), stream))
+        assert k0.value == done_out
+        g.filt_(y[done_out:], x[done_in:])
+    return y

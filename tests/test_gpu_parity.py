@@ -450,3 +450,22 @@ def test_fast_paths_random_stress_against_generic_kernel(rng):
             used.add(f.last_kernel)
         torch.cuda.synchronize()
         assert any(k.startswith(want) for k in used) or n < 2000, (ratio, ntaps, nch, used)
+
+
+@pytest.mark.parametrize("case", ["rational", "decimator", "interpolator"])
+def test_long_stream_in_place_segmentation(case, rng):
+    """filt_long_stream: one long stream viewed in place as a matrix of M-aligned segments (halo = the samples
+    that precede each segment in memory) equals the plain single-channel call; counts exact."""
+    import torch
+    cfg = {"rational": (Fraction(147, 160), mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32), np.complex64),
+           "decimator": (Fraction(1, 8), mo.firdes(256, 0.5 / 8, 7.8562).astype(np.float32), np.complex64),
+           "interpolator": (Fraction(4, 1), mo.firdes(128, 0.5 / 4, 7.8562).astype(np.float32), np.float32)}[case]
+    ratio, h, tx = cfg
+    n = 1_500_017
+    x = torch.from_numpy(rand_samples(rng, (n,), tx)).cuda()
+    whole = mr.FIRFilter(h, ratio).filt(x)
+    got = mr.filt_long_stream(h, ratio, x, rows_target=96)
+    assert got.shape == whole.shape
+    assert (got - whole).abs().max().item() <= 2e-6 * whole.abs().max().item()
+    w = mo.filt(h, x[:30000].cpu().numpy(), ratio)
+    assert nerr(got[:w.shape[0]].cpu().numpy(), w) <= 1e-5
