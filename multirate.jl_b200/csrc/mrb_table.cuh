@@ -26,19 +26,20 @@ namespace mrb {
 constexpr int kTabRows = 32;            // channels per CTA
 constexpr int kTabStep = 32;            // outputs per CTA step
 constexpr int kTabWarps = 4;
+constexpr int kTabGroup = 8;            // consecutive outputs that share one register window (one warp's share of a step)
 
 template <typename R> struct TabCfg;
 template <> struct TabCfg<float> {
     static constexpr int A = 4;         // elements per 16 bytes
-    static constexpr int TB = 80;       // taps (row elements) per block
+    static constexpr int TB = 96;       // row elements per block
     static constexpr int BOXE = 32;     // elements per box row (128 B)
     static constexpr int NB = 10;       // ring boxes
 };
 template <> struct TabCfg<double> {
     static constexpr int A = 2;
-    static constexpr int TB = 40;
+    static constexpr int TB = 48;
     static constexpr int BOXE = 16;
-    static constexpr int NB = 16;
+    static constexpr int NB = 14;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -54,8 +55,11 @@ k_table_rows(const R *__restrict__ pfb, const R *__restrict__ dpfb, const double
     if (idx >= nout * rowlen) return;
     const int64_t k = idx / rowlen;
     const int j = (int)(idx - k * rowlen);
+    // the kTabGroup outputs of a group read ONE register window that starts at the aligned window start of the
+    // group's first output; every row of the group is shifted to its own place inside that window
     const int64_t xs = sn[k] - H;                                    // x index of the window start (may be < 0: head)
-    const int64_t al = xs >= 0 ? xs / A * A : -((-xs + A - 1) / A) * A;
+    const int64_t xg = sn[k / kTabGroup * kTabGroup] - H;
+    const int64_t al = xg >= 0 ? xg / A * A : -((-xg + A - 1) / A) * A;
     const int d = (int)(xs - al);
     if (j == 0) astart[k] = (int32_t)al;
     const int i = j - d;
@@ -92,7 +96,7 @@ struct alignas(16) TabParams {
 };
 
 template <typename R>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 3)
 k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
             const R *__restrict__ rows, const int32_t *__restrict__ astart, const __grid_constant__ TabParams P) {
     using C = TabCfg<R>;
@@ -154,18 +158,20 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         mbar_wait(rbar_base + 8 * rslot, (uint32_t)((s >> 1) & 1));  // this step's tap rows are in shared memory
         const R *rows_step = reinterpret_cast<const R *>(rows_s + rslot * row_bytes);
         const int *ast_step = ast_s + rslot * kTabStep;
-#pragma unroll 1
-        for (int o = 0; o < OPW; ++o) {
-            const long long k = ks + warp * OPW + o;
-            R acc0 = R(0), acc1 = R(0), acc2 = R(0), acc3 = R(0);
-            if (k <= klast) {
-                const int a0 = ast_step[warp * OPW + o] - xbase;     // tile-relative aligned window start (elements)
+        {
+            static_assert(OPW == kTabGroup, "a warp's share of a step is one window group");
+            const long long kg = ks + warp * OPW;                    // first output of this warp's group
+            R acc[OPW][2];
+#pragma unroll
+            for (int o = 0; o < OPW; ++o) acc[o][0] = acc[o][1] = R(0);
+            if (kg <= klast) {
+                const int a0 = ast_step[warp * OPW] - xbase;         // tile-relative aligned window start (elements)
                 const int need = (a0 + P.rowlen - 1) / C::BOXE;
                 for (; j_waited <= need; ++j_waited) {
                     mbar_wait(bar_base + 8 * w_slot, w_par);
                     if (++w_slot == NB) { w_slot = 0; w_par ^= 1u; }
                 }
-                const R *row = rows_step + (warp * OPW + o) * P.rowlen;
+                const R *rowg = rows_step + (warp * OPW) * P.rowlen;
                 for (int bb = 0; bb < P.nblk; ++bb) {
                     const int p = ((a0 + bb * TB) / A) % (8 * NB);   // ring position in 16-byte chunks
                     const unsigned *wt = P.win[p & 3] + (p & ~3);
@@ -187,30 +193,36 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                             }
                         }
                     }
-                    const R *tr = row + bb * TB;
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        if constexpr (A == 4) {
-                            const float4 t = reinterpret_cast<const float4 *>(tr)[q];
-                            acc0 = fmaf(t.x, w[4 * q], acc0);
-                            acc1 = fmaf(t.y, w[4 * q + 1], acc1);
-                            acc2 = fmaf(t.z, w[4 * q + 2], acc2);
-                            acc3 = fmaf(t.w, w[4 * q + 3], acc3);
-                        } else {
-                            const double2 t = reinterpret_cast<const double2 *>(tr)[q];
-                            if (q & 1) { acc2 = fma(t.x, w[2 * q], acc2); acc3 = fma(t.y, w[2 * q + 1], acc3); }
-                            else { acc0 = fma(t.x, w[2 * q], acc0); acc1 = fma(t.y, w[2 * q + 1], acc1); }
+                    for (int o = 0; o < OPW; ++o) {
+                        const R *tr = rowg + o * P.rowlen + bb * TB;
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            if constexpr (A == 4) {
+                                const float4 t = reinterpret_cast<const float4 *>(tr)[q];
+                                acc[o][0] = fmaf(t.x, w[4 * q], acc[o][0]);
+                                acc[o][1] = fmaf(t.y, w[4 * q + 1], acc[o][1]);
+                                acc[o][0] = fmaf(t.z, w[4 * q + 2], acc[o][0]);
+                                acc[o][1] = fmaf(t.w, w[4 * q + 3], acc[o][1]);
+                            } else {
+                                const double2 t = reinterpret_cast<const double2 *>(tr)[q];
+                                acc[o][0] = fma(t.x, w[2 * q], acc[o][0]);
+                                acc[o][1] = fma(t.y, w[2 * q + 1], acc[o][1]);
+                            }
                         }
                     }
                 }
             }
             // stage: row = channel, column = output within the step; 128-byte swizzle atoms of 32/16 outputs
-            const int col = warp * OPW + o;
-            const uint32_t byte = (uint32_t)col * sizeof(R);
-            const uint32_t ad = obase + (byte >> 7) * (kTabRows * 128u) + (rowpart ^ (((byte >> 4) & 7u) << 4)) + (byte & 15u);
-            const R y = (acc0 + acc1) + (acc2 + acc3);
-            if constexpr (A == 4) asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(y) : "memory");
-            else asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(y) : "memory");
+#pragma unroll
+            for (int o = 0; o < OPW; ++o) {
+                const int col = warp * OPW + o;
+                const uint32_t byte = (uint32_t)col * sizeof(R);
+                const uint32_t ad = obase + (byte >> 7) * (kTabRows * 128u) + (rowpart ^ (((byte >> 4) & 7u) << 4)) + (byte & 15u);
+                const R y = acc[o][0] + acc[o][1];
+                if constexpr (A == 4) asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(y) : "memory");
+                else asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(y) : "memory");
+            }
         }
 
         // ---- the step's outputs leave; boxes before the next step's first window are refilled
@@ -277,11 +289,11 @@ static inline int table_smem(int rowlen) {
 }
 
 // kind/tx/ty are the mrb.h enums (4 arbitrary, 5 farrow ; 0 = float32, 1 = float64)
-static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_t T, const cudaDeviceProp &prop) {
+static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_t T, double rate, const cudaDeviceProp &prop) {
     p.ok = false;
     if (!(kind == 4 || kind == 5)) return 0;
     if (!((tx == 0 && ty == 0) || (tx == 1 && ty == 1))) return 0;      // real samples, no promotion
-    if (T + 3 > 2 * (ty == 1 ? TabCfg<double>::TB : TabCfg<float>::TB)) return 0;   // two tap blocks: staged rows fit
+    if (T + 3 > 2 * (ty == 1 ? TabCfg<double>::TB : TabCfg<float>::TB)) return 0;   // two blocks: staged rows fit
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -291,7 +303,10 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
     p.dbl = ty == 1;
     p.T = (int)T;
     const int TB = p.dbl ? TabCfg<double>::TB : TabCfg<float>::TB, A = p.dbl ? 2 : 4;
-    p.nblk = (int)ceil_div(T + A - 1, TB);                              // room for the alignment shift d_k < A
+    // a group's rows are shifted by up to (A-1) + (window start of its last output - that of its first)
+    const int64_t gspan = rate > 0.0 ? (int64_t)std::ceil((kTabGroup - 1) / rate) + 1 : (int64_t)1 << 20;
+    p.nblk = (int)ceil_div(T + A - 1 + gspan, TB);
+    if (p.nblk > 2) return 0;                                            // rate too low for a shared window
     p.rowlen = p.nblk * TB;
     p.hp = new TabParams();
     memset(p.hp, 0, sizeof(TabParams));
@@ -327,7 +342,7 @@ static inline cudaError_t table_reserve(TabPlan &p, int64_t nout) {
 // (the caller computes the slice's outputs before it with the generic kernel), -1 when not covered, -2 on error.
 static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind, int P1, int tap_is_f32,
                                        const void *d_pfb, const void *d_dpfb, const double *d_pnfb, double rate, int64_t y0, int64_t cnt,
-                                       int64_t head, cudaStream_t st, const char **name, int64_t *launches) {
+                                       int64_t head, int64_t max_group_span, cudaStream_t st, const char **name, int64_t *launches) {
     static const bool trace = getenv("MRB_TRACE") != nullptr;
 #define MRB_TAB_SKIP(why) do { if (trace) fprintf(stderr, "[mrb] table kernel not used: %s\n", why); return -1; } while (0)
     if (!p.ok) MRB_TAB_SKIP("configuration not covered");
@@ -335,6 +350,7 @@ static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind,
     if (((uintptr_t)G.x & 15) || ((uintptr_t)G.y & 15) || (G.ldx % A) || (G.ldy % A)) MRB_TAB_SKIP("alignment");
     if (G.n_in >= (1ll << 31) - 4096 || y0 + cnt >= (1ll << 31) - 4096) MRB_TAB_SKIP("size");
     if (y0 % kTabStep) MRB_TAB_SKIP("slice start");
+    if (max_group_span + p.T + A - 1 > p.rowlen) MRB_TAB_SKIP("window group wider than the tap rows");
     {   // a step's windows (32 outputs) plus two boxes of refill room must fit the ring
         const int BOXE = 128 / es, NB = p.dbl ? TabCfg<double>::NB : TabCfg<float>::NB;
         const double span = (double)kTabStep / rate + p.rowlen + 2.0 * BOXE;
