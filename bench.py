@@ -186,10 +186,12 @@ def run_reference(args):
         return
     w = args.workload
     r = cpu_port_run(w, args.steps, max(args.warmup, 1), target_s=20.0)
-    line = {"metric": "output Msamples/s (multichannel)", "value": r["value"], "unit": "Msamples/s", "impl": "reference",
+    desc, ratio, ntaps, cutoff, beta, gain, tx, nch_default, nphi, po = WORKLOADS[w]
+    line = {"metric": "output Msamples/s (multichannel, device-timed)", "value": r["value"], "unit": "Msamples/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_name(w), "data": "synthetic",
-            "config": {"workload": WORKLOADS[w][0], "timed": "bounded sample on host cores: " + r["sample"]},
+            "config": {"workload": desc, "channels_per_gpu": nch_default, "chunk_samples": chunk_len(w), "taps": ntaps,
+                       "timed": "bounded sample of that workload on the host cores: " + r["sample"]},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
