@@ -6,7 +6,7 @@ through a stateful FIRFilter (history, phase and deficit carried on the device b
 
 Default workload (N=1 and every N, weak scaling): BASELINE.json configs[4]'s per-GPU shard --
 FIRRational 147//160, 3528-tap Kaiser low-pass (Float32 taps), 8192 channels of Complex64 per GPU
-(65,536 channels over 8 GPUs), 64K-sample chunks.  Other configs: --workload c1|c2|c3a|c3b|c4a|c4f.
+(65,536 channels over 8 GPUs), 64K-sample chunks.  Other configs: --workload c1|c2|c3a|c3b|c4a|c4f|c4a64|c4f64.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5] [--impl reference]
 """
@@ -44,6 +44,10 @@ WORKLOADS = {
             0.918734, 2336, 0.45 / 32, 5.6533, 32.0, np.float32, 1024, 32, None),
     "c4f": ("FIRFarrow rate 0.918734, Nphi 32, 2336 taps, order 4, 1024 ch float32 (BASELINE configs[3])",
             0.918734, 2336, 0.45 / 32, 5.6533, 32.0, np.float32, 1024, 32, 4),
+    "c4a64": ("FIRArbitrary rate 0.918734, Nphi 32, 2336 taps, 1024 ch float64 (BASELINE configs[3])",
+              0.918734, 2336, 0.45 / 32, 5.6533, 32.0, np.float64, 1024, 32, None),
+    "c4f64": ("FIRFarrow rate 0.918734, Nphi 32, 2336 taps, order 4, 1024 ch float64 (BASELINE configs[3])",
+              0.918734, 2336, 0.45 / 32, 5.6533, 32.0, np.float64, 1024, 32, 4),
 }
 
 
@@ -113,6 +117,8 @@ class ClockSampler:
 def make_filter(mr, w, nch=None, device=0):
     desc, ratio, ntaps, cutoff, beta, gain, tx, nch_default, nphi, po = WORKLOADS[w]
     h = design_taps(ntaps, cutoff, beta, gain)
+    if np.dtype(tx) == np.float64:
+        h = h.astype(np.float64)                          # Float64 taps with Float64 samples
     nch = nch or nch_default
     if isinstance(ratio, float):
         return mr.FIRFilter(h, ratio, nphi, po, nchannels=nch, sample_dtype=tx, device=device), h
@@ -136,6 +142,8 @@ def cpu_port_run(w, steps, warmup, target_s=6.0):
         native = False
     desc, ratio, ntaps, cutoff, beta, gain, tx, nch_default, nphi, po = WORKLOADS[w]
     h = design_taps(ntaps, cutoff, beta, gain)
+    if np.dtype(tx) == np.float64:
+        h = h.astype(np.float64)
     threads = os.cpu_count() or 1
     n = chunk_len(w)
     rng = np.random.default_rng(0x4D520000)
@@ -271,7 +279,8 @@ def main():
     if np.dtype(tx).kind == "c":
         x = torch.view_as_complex(torch.rand((nch, n, 2), generator=gen, device="cuda", dtype=torch.float32))
     else:
-        x = torch.rand((nch, n), generator=gen, device="cuda", dtype=torch.float32)
+        x = torch.rand((nch, n), generator=gen, device="cuda",
+                       dtype=torch.float64 if np.dtype(tx) == np.float64 else torch.float32)
     n_out_max = (f.outputlength(n) + 2 + 3) // 4 * 4                  # row pitch: a multiple of 16 bytes (TMA)
     ybuf = torch.empty((nch, n_out_max), dtype=x.dtype, device="cuda")
     es = x.element_size()
@@ -327,7 +336,7 @@ def main():
                 "peak_source": peak_src}
     # FP32 side of the roofline: real FMAs the kernel executes per output and channel.  Only the 147//160
     # shard (c5) is HBM-bound; decimator-256, standard-128 and the arbitrary-rate kernels sit on the FP32 roof.
-    taps_per_out = {"c5": 24, "c1": 24, "c2": 256, "c3a": 32, "c3b": 128, "c4a": 73, "c4f": 73}[w]
+    taps_per_out = {"c5": 24, "c1": 24, "c2": 256, "c3a": 32, "c3b": 128, "c4a": 73, "c4f": 73, "c4a64": 73, "c4f64": 73}[w]
     flops = 2 * taps_per_out * (2 if np.dtype(tx).kind == "c" else 1)
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                       # nominal, TFLOP/s
     if kms:
@@ -336,7 +345,9 @@ def main():
                             "frac": tf / fp32_peak,
                             "note": "arbitrary: taps blended once per output (73 FMAs), the reference does two dot products"
                                     if w == "c4a" else None}
-        if w in ("c2", "c3b", "c4a", "c4f"):
+        if w.startswith("c4") and w.endswith("64"):
+            roofline["fp32"]["note"] = "Float64 FMAs; the nominal FP64 peak is half the FP32 figure"
+        if w in ("c2", "c3b", "c4a", "c4f", "c4a64", "c4f64"):
             roofline["bound"] = "fp32 (see roofline.fp32; hbm fields kept for reference)"
     tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % w)
     if os.path.exists(tr):

@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 o=gpurun_out
 timeout 600 python -m pytest tests -m gpu -q --timeout 120 2>&1 | tail -3 > $o/r1_pytest_gpu.txt
 timeout 400 python bench.py --steps 20 --warmup 3 > $o/r1_bench_c5_n1.json 2> $o/r1_bench_c5_n1.err
-for w in c1 c2 c3a c3b c4a c4f; do
+for w in c1 c2 c3a c3b c4a c4f c4a64 c4f64; do
   timeout 300 python bench.py --workload $w --steps 20 --warmup 3 --no-e2e > $o/r1_bench_$w.json 2> $o/r1_bench_$w.err
 done
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $o/r1_bench_reference_arm.json 2>> $o/r1_bench_c5_n1.err
