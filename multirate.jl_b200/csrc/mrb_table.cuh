@@ -28,14 +28,28 @@ constexpr int kTabStep = 32;            // outputs per CTA step
 constexpr int kTabWarps = 4;
 constexpr int kTabGroup = 8;            // consecutive outputs that share one register window (one warp's share of a step)
 
-template <typename R> struct TabCfg;
-template <> struct TabCfg<float> {
-    static constexpr int A = 4;         // elements per 16 bytes
-    static constexpr int TB = 96;       // row elements per block
-    static constexpr int BOXE = 32;     // elements per box row (128 B)
+// sample kinds the kernel is instantiated for
+enum { TAB_F32 = 0, TAB_F64 = 1, TAB_C64 = 2 };
+template <int K> struct TabCfg;
+template <> struct TabCfg<TAB_F32> {
+    using Tap = float;                  // tap-row element
+    static constexpr int ES = 4;        // bytes per sample
+    static constexpr int A = 4;         // samples per 16 bytes
+    static constexpr int TB = 96;       // row elements (window samples) per block
+    static constexpr int BOXE = 32;     // samples per box row (128 B)
     static constexpr int NB = 10;       // ring boxes
 };
-template <> struct TabCfg<double> {
+template <> struct TabCfg<TAB_F64> {
+    using Tap = double;
+    static constexpr int ES = 8;
+    static constexpr int A = 2;
+    static constexpr int TB = 48;
+    static constexpr int BOXE = 16;
+    static constexpr int NB = 14;
+};
+template <> struct TabCfg<TAB_C64> {    // complex64 samples x float32 taps: two FMAs per tap
+    using Tap = float;
+    static constexpr int ES = 8;
     static constexpr int A = 2;
     static constexpr int TB = 48;
     static constexpr int BOXE = 16;
@@ -49,8 +63,8 @@ template <typename R>
 __global__ void __launch_bounds__(256)
 k_table_rows(const R *__restrict__ pfb, const R *__restrict__ dpfb, const double *__restrict__ pnfb, int P1, int T,
              int rowlen, int farrow, int tap_is_f32, const int64_t *__restrict__ sn, const int32_t *__restrict__ sphi,
-             const double *__restrict__ sa, int64_t H, int64_t nout, R *__restrict__ rows, int32_t *__restrict__ astart) {
-    constexpr int A = TabCfg<R>::A;
+             const double *__restrict__ sa, int64_t H, int64_t nout, R *__restrict__ rows, int32_t *__restrict__ astart,
+             int A) {
     const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (idx >= nout * rowlen) return;
     const int64_t k = idx / rowlen;
@@ -95,20 +109,22 @@ struct alignas(16) TabParams {
     unsigned win[4][160];      // win[c][i] = W((c + i) mod 8 NB): chunk bits | ring slot offset of 16-byte chunk u
 };
 
-template <typename R>
+template <int K>
 __global__ void __launch_bounds__(128, 3)
 k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
-            const R *__restrict__ rows, const int32_t *__restrict__ astart, const __grid_constant__ TabParams P) {
-    using C = TabCfg<R>;
-    constexpr int A = C::A, TB = C::TB, NQ = TB / A, NB = C::NB;
+            const typename TabCfg<K>::Tap *__restrict__ rows, const int32_t *__restrict__ astart,
+            const __grid_constant__ TabParams P) {
+    using C = TabCfg<K>;
+    using R = typename C::Tap;
+    constexpr int A = C::A, TB = C::TB, NQ = TB / A, NB = C::NB, ES = C::ES;
     constexpr int BOX_BYTES = kTabRows * 128;
     constexpr int OPW = kTabStep / kTabWarps;                        // outputs per warp per step
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *out_buf = smem + NB * BOX_BYTES;                  // [32 ch][32 outputs] R, 128-byte swizzle atoms
+    unsigned char *out_buf = smem + NB * BOX_BYTES;                  // [32 ch][32 outputs], 128-byte swizzle atoms
     // the tap rows and aligned window starts of a step (32 outputs), double buffered, fetched by bulk copies a
     // step ahead: the taps are then read with warp-uniform LDS.128 instead of L2-latency global loads
-    const int row_bytes = kTabStep * P.rowlen * (int)sizeof(R);
-    unsigned char *rows_s = out_buf + kTabRows * kTabStep * sizeof(R);
+    const int row_bytes = kTabStep * P.rowlen * (int)sizeof(R);      // R = tap type
+    unsigned char *rows_s = out_buf + kTabRows * kTabStep * ES;
     int *ast_s = reinterpret_cast<int *>(rows_s + 2 * row_bytes);    // [2][32]
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(ast_s + 2 * kTabStep);
 
@@ -161,11 +177,12 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         {
             static_assert(OPW == kTabGroup, "a warp's share of a step is one window group");
             const long long kg = ks + warp * OPW;                    // first output of this warp's group
+            // f32 / f64: two partial sums per output; c64: real and imaginary part
             R acc[OPW][2];
 #pragma unroll
             for (int o = 0; o < OPW; ++o) acc[o][0] = acc[o][1] = R(0);
             if (kg <= klast) {
-                const int a0 = ast_step[warp * OPW] - xbase;         // tile-relative aligned window start (elements)
+                const int a0 = ast_step[warp * OPW] - xbase;         // tile-relative aligned window start (samples)
                 const int need = (a0 + P.rowlen - 1) / C::BOXE;
                 for (; j_waited <= need; ++j_waited) {
                     mbar_wait(bar_base + 8 * w_slot, w_par);
@@ -175,7 +192,8 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                 for (int bb = 0; bb < P.nblk; ++bb) {
                     const int p = ((a0 + bb * TB) / A) % (8 * NB);   // ring position in 16-byte chunks
                     const unsigned *wt = P.win[p & 3] + (p & ~3);
-                    R w[TB];
+                    constexpr int WR = K == TAB_C64 ? 2 * TB : TB;   // window registers of type R
+                    R w[WR];
 #pragma unroll
                     for (int q = 0; q < NQ; q += 4) {
                         const uint4 w4 = *reinterpret_cast<const uint4 *>(wt + q);
@@ -183,31 +201,43 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const uint32_t ad = in_base + (rowpart ^ ww[e]);
-                            if constexpr (A == 4) {
+                            if constexpr (K == TAB_F64) {
+                                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                                             : "=d"(w[2 * (q + e)]), "=d"(w[2 * (q + e) + 1]) : "r"(ad) : "memory");
+                            } else {                                 // four floats: 4 real samples or 2 complex ones
                                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                              : "=f"(w[4 * (q + e)]), "=f"(w[4 * (q + e) + 1]), "=f"(w[4 * (q + e) + 2]),
                                                "=f"(w[4 * (q + e) + 3]) : "r"(ad) : "memory");
-                            } else {
-                                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
-                                             : "=d"(w[2 * (q + e)]), "=d"(w[2 * (q + e) + 1]) : "r"(ad) : "memory");
                             }
                         }
                     }
 #pragma unroll
                     for (int o = 0; o < OPW; ++o) {
                         const R *tr = rowg + o * P.rowlen + bb * TB;
+                        if constexpr (K == TAB_F32) {
 #pragma unroll
-                        for (int q = 0; q < NQ; ++q) {
-                            if constexpr (A == 4) {
+                            for (int q = 0; q < TB / 4; ++q) {
                                 const float4 t = reinterpret_cast<const float4 *>(tr)[q];
                                 acc[o][0] = fmaf(t.x, w[4 * q], acc[o][0]);
                                 acc[o][1] = fmaf(t.y, w[4 * q + 1], acc[o][1]);
                                 acc[o][0] = fmaf(t.z, w[4 * q + 2], acc[o][0]);
                                 acc[o][1] = fmaf(t.w, w[4 * q + 3], acc[o][1]);
-                            } else {
+                            }
+                        } else if constexpr (K == TAB_F64) {
+#pragma unroll
+                            for (int q = 0; q < TB / 2; ++q) {
                                 const double2 t = reinterpret_cast<const double2 *>(tr)[q];
                                 acc[o][0] = fma(t.x, w[2 * q], acc[o][0]);
                                 acc[o][1] = fma(t.y, w[2 * q + 1], acc[o][1]);
+                            }
+                        } else {                                     // complex sample i = (w[2i], w[2i+1]), real tap
+#pragma unroll
+                            for (int q = 0; q < TB / 4; ++q) {
+                                const float4 t = reinterpret_cast<const float4 *>(tr)[q];
+                                acc[o][0] = fmaf(t.x, w[8 * q], acc[o][0]);     acc[o][1] = fmaf(t.x, w[8 * q + 1], acc[o][1]);
+                                acc[o][0] = fmaf(t.y, w[8 * q + 2], acc[o][0]); acc[o][1] = fmaf(t.y, w[8 * q + 3], acc[o][1]);
+                                acc[o][0] = fmaf(t.z, w[8 * q + 4], acc[o][0]); acc[o][1] = fmaf(t.z, w[8 * q + 5], acc[o][1]);
+                                acc[o][0] = fmaf(t.w, w[8 * q + 6], acc[o][0]); acc[o][1] = fmaf(t.w, w[8 * q + 7], acc[o][1]);
                             }
                         }
                     }
@@ -217,11 +247,15 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 #pragma unroll
             for (int o = 0; o < OPW; ++o) {
                 const int col = warp * OPW + o;
-                const uint32_t byte = (uint32_t)col * sizeof(R);
+                const uint32_t byte = (uint32_t)col * ES;
                 const uint32_t ad = obase + (byte >> 7) * (kTabRows * 128u) + (rowpart ^ (((byte >> 4) & 7u) << 4)) + (byte & 15u);
-                const R y = acc[o][0] + acc[o][1];
-                if constexpr (A == 4) asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(y) : "memory");
-                else asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(y) : "memory");
+                if constexpr (K == TAB_F32) {
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(acc[o][0] + acc[o][1]) : "memory");
+                } else if constexpr (K == TAB_F64) {
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(acc[o][0] + acc[o][1]) : "memory");
+                } else {
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ad), "f"(acc[o][0]), "f"(acc[o][1]) : "memory");
+                }
             }
         }
 
@@ -232,7 +266,7 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         const int jdead = (astart[kn] - xbase) / C::BOXE;            // oldest box the next step reads
         const int jtarget = min(jdead + NB - 1, jlast);
         if (tid == 0) {
-            constexpr int NST = (int)(kTabStep * sizeof(R) / 128);   // 128-byte-wide sub-boxes per step
+            constexpr int NST = kTabStep * ES / 128;                 // 128-byte-wide sub-boxes per step
             for (int b = 0; b < NST; ++b)
                 tma_store_2d(&tmy, (int)(P.y0 + ks) + b * C::BOXE, ch0, obase + (uint32_t)(b * kTabRows * 128));
             tma_commit();
@@ -264,11 +298,12 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------------------
 struct TabPlan {
     bool ok = false;
-    bool dbl = false;
+    int K = TAB_F32;                   // sample kind the plan was built for
+    int es = 4, ts = 4, A = 4, TB = 96, NB = 10;   // sample bytes, tap bytes, samples per 16 B, block, ring boxes
     int T = 0, nblk = 0, rowlen = 0;
     TabParams *hp = nullptr;
     PFN_encodeTiled encode = nullptr;
-    void *d_rows = nullptr;            // R[slice outputs][rowlen]
+    void *d_rows = nullptr;            // Tap[slice outputs][rowlen]
     int32_t *d_astart = nullptr;
     int64_t cap = 0;                   // outputs the two buffers hold
     int num_sms = 148;
@@ -282,43 +317,44 @@ static inline void table_release(TabPlan &p) {
     p.ok = false;
 }
 
-template <typename R>
-static inline int table_smem(int rowlen) {
-    return TabCfg<R>::NB * kTabRows * 128 + kTabRows * kTabStep * (int)sizeof(R) + 2 * kTabStep * rowlen * (int)sizeof(R) +
-           2 * kTabStep * 4 + 8 * (TabCfg<R>::NB + 2);
+static inline int table_smem(const TabPlan &p) {
+    return p.NB * kTabRows * 128 + kTabRows * kTabStep * p.es + 2 * kTabStep * p.rowlen * p.ts + 2 * kTabStep * 4 +
+           8 * (p.NB + 2);
 }
 
-// kind/tx/ty are the mrb.h enums (4 arbitrary, 5 farrow ; 0 = float32, 1 = float64)
+// kind/tx/ty are the mrb.h enums (4 arbitrary, 5 farrow ; 0 = float32, 1 = float64, 2 = complex64)
 static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_t T, double rate, const cudaDeviceProp &prop) {
     p.ok = false;
     if (!(kind == 4 || kind == 5)) return 0;
-    if (!((tx == 0 && ty == 0) || (tx == 1 && ty == 1))) return 0;      // real samples, no promotion
-    if (T + 3 > 2 * (ty == 1 ? TabCfg<double>::TB : TabCfg<float>::TB)) return 0;   // two blocks: staged rows fit
+    if (tx != ty || !(tx == 0 || tx == 1 || tx == 2)) return 0;         // float32, float64, complex64; no promotion
+    p.K = tx == 0 ? TAB_F32 : tx == 1 ? TAB_F64 : TAB_C64;
+    if (p.K == TAB_F32) { p.es = 4; p.ts = 4; p.A = 4; p.TB = TabCfg<TAB_F32>::TB; p.NB = TabCfg<TAB_F32>::NB; }
+    else if (p.K == TAB_F64) { p.es = 8; p.ts = 8; p.A = 2; p.TB = TabCfg<TAB_F64>::TB; p.NB = TabCfg<TAB_F64>::NB; }
+    else { p.es = 8; p.ts = 4; p.A = 2; p.TB = TabCfg<TAB_C64>::TB; p.NB = TabCfg<TAB_C64>::NB; }
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int32_t)(e ? e : cudaErrorUnknown);
     p.encode = (PFN_encodeTiled)fn;
     p.num_sms = prop.multiProcessorCount;
-    p.dbl = ty == 1;
     p.T = (int)T;
-    const int TB = p.dbl ? TabCfg<double>::TB : TabCfg<float>::TB, A = p.dbl ? 2 : 4;
     // a group's rows are shifted by up to (A-1) + (window start of its last output - that of its first)
     const int64_t gspan = rate > 0.0 ? (int64_t)std::ceil((kTabGroup - 1) / rate) + 1 : (int64_t)1 << 20;
-    p.nblk = (int)ceil_div(T + A - 1 + gspan, TB);
-    if (p.nblk > 2) return 0;                                            // rate too low for a shared window
-    p.rowlen = p.nblk * TB;
+    p.nblk = (int)ceil_div(T + p.A - 1 + gspan, p.TB);
+    if (p.nblk > 2) return 0;                                            // taps too long / rate too low for a shared window
+    p.rowlen = p.nblk * p.TB;
     p.hp = new TabParams();
     memset(p.hp, 0, sizeof(TabParams));
     p.hp->nblk = p.nblk; p.hp->rowlen = p.rowlen;
-    const int NB = p.dbl ? TabCfg<double>::NB : TabCfg<float>::NB;
     for (int c = 0; c < 4; ++c)
         for (int i = 0; i < 160; ++i) {
-            const unsigned u = (unsigned)(c + i) % (unsigned)(8 * NB);
+            const unsigned u = (unsigned)(c + i) % (unsigned)(8 * p.NB);
             p.hp->win[c][i] = ((u & 7u) << 4) | ((u >> 3) * (unsigned)(kTabRows * 128));
         }
-    e = p.dbl ? cudaFuncSetAttribute(k_table_fir<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, table_smem<double>(p.rowlen))
-              : cudaFuncSetAttribute(k_table_fir<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, table_smem<float>(p.rowlen));
+    const int smem = table_smem(p);
+    e = p.K == TAB_F32 ? cudaFuncSetAttribute(k_table_fir<TAB_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+      : p.K == TAB_F64 ? cudaFuncSetAttribute(k_table_fir<TAB_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                       : cudaFuncSetAttribute(k_table_fir<TAB_C64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int32_t)e;
     p.ok = true;
     return 0;
@@ -329,7 +365,7 @@ static inline cudaError_t table_reserve(TabPlan &p, int64_t nout) {
     cudaFree(p.d_rows); cudaFree(p.d_astart);
     p.d_rows = nullptr; p.d_astart = nullptr; p.cap = 0;
     // two steps of slack: the kernel stages whole steps (32 rows) of the table
-    cudaError_t e = cudaMalloc(&p.d_rows, (size_t)(nout + 2 * kTabStep) * p.rowlen * (p.dbl ? 8 : 4));
+    cudaError_t e = cudaMalloc(&p.d_rows, (size_t)(nout + 2 * kTabStep) * p.rowlen * p.ts);
     if (e != cudaSuccess) return e;
     e = cudaMalloc(&p.d_astart, (size_t)(nout + 2 * kTabStep) * sizeof(int32_t));
     if (e != cudaSuccess) return e;
@@ -346,15 +382,14 @@ static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind,
     static const bool trace = getenv("MRB_TRACE") != nullptr;
 #define MRB_TAB_SKIP(why) do { if (trace) fprintf(stderr, "[mrb] table kernel not used: %s\n", why); return -1; } while (0)
     if (!p.ok) MRB_TAB_SKIP("configuration not covered");
-    const int es = p.dbl ? 8 : 4, A = 16 / es;
+    const int es = p.es, A = p.A, BOXE = 128 / es;
     if (((uintptr_t)G.x & 15) || ((uintptr_t)G.y & 15) || (G.ldx % A) || (G.ldy % A)) MRB_TAB_SKIP("alignment");
     if (G.n_in >= (1ll << 31) - 4096 || y0 + cnt >= (1ll << 31) - 4096) MRB_TAB_SKIP("size");
     if (y0 % kTabStep) MRB_TAB_SKIP("slice start");
     if (max_group_span + p.T + A - 1 > p.rowlen) MRB_TAB_SKIP("window group wider than the tap rows");
     {   // a step's windows (32 outputs) plus two boxes of refill room must fit the ring
-        const int BOXE = 128 / es, NB = p.dbl ? TabCfg<double>::NB : TabCfg<float>::NB;
         const double span = (double)kTabStep / rate + p.rowlen + 2.0 * BOXE;
-        if (!(rate > 0.0) || span > (double)(NB - 2) * BOXE) MRB_TAB_SKIP("rate too low for the ring");
+        if (!(rate > 0.0) || span > (double)(p.NB - 2) * BOXE) MRB_TAB_SKIP("rate too low for the ring");
     }
     const int64_t k_begin = (head + kTabStep - 1) / kTabStep * kTabStep;
     if (cnt - k_begin < 4 * kTabStep) MRB_TAB_SKIP("slice too short");
@@ -363,14 +398,14 @@ static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind,
     {   // pre-pass: rows + aligned starts for the whole slice (the head rows are not used)
         const int64_t total = cnt * p.rowlen;
         const unsigned g = (unsigned)ceil_div(total, 256);
-        if (p.dbl)
+        if (p.K == TAB_F64)
             k_table_rows<double><<<g, 256, 0, st>>>((const double *)d_pfb, (const double *)d_dpfb, d_pnfb, P1, p.T, p.rowlen,
                                                     kind == 5, tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt,
-                                                    (double *)p.d_rows, p.d_astart);
+                                                    (double *)p.d_rows, p.d_astart, A);
         else
             k_table_rows<float><<<g, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, p.rowlen,
                                                    kind == 5, tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt,
-                                                   (float *)p.d_rows, p.d_astart);
+                                                   (float *)p.d_rows, p.d_astart, A);
         ++*launches;
     }
     TabParams &P = *p.hp;
@@ -381,11 +416,12 @@ static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind,
     P.KT = (int)(ceil_div(ceil_div(span, tiles), kTabStep) * kTabStep);
     tiles = ceil_div(span, P.KT);
 
+    // complex64 moves through TMA as 8-byte elements (no arithmetic on the way)
     CUtensorMap tmx, tmy;
-    const CUtensorMapDataType dt = p.dbl ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapDataType dt = es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     cuuint64_t dims[2] = {(cuuint64_t)G.n_in, (cuuint64_t)G.nch};
     cuuint64_t strides[1] = {(cuuint64_t)G.ldx * es};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / es), kTabRows};
+    cuuint32_t box[2] = {(cuuint32_t)BOXE, kTabRows};
     cuuint32_t ones[2] = {1, 1};
     if (p.encode(&tmx, dt, 2, const_cast<void *>(G.x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -397,10 +433,12 @@ static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind,
         MRB_TAB_SKIP("y tensor map");
 #undef MRB_TAB_SKIP
     dim3 grid((unsigned)groups, (unsigned)tiles);
-    if (p.dbl) k_table_fir<double><<<grid, 128, table_smem<double>(p.rowlen), st>>>(tmx, tmy, (const double *)p.d_rows, p.d_astart, P);
-    else k_table_fir<float><<<grid, 128, table_smem<float>(p.rowlen), st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+    const int smem = table_smem(p);
+    if (p.K == TAB_F32) k_table_fir<TAB_F32><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+    else if (p.K == TAB_F64) k_table_fir<TAB_F64><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)p.d_rows, p.d_astart, P);
+    else k_table_fir<TAB_C64><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
-    *name = p.dbl ? "table_f64" : "table_f32";
+    *name = p.K == TAB_F32 ? "table_f32" : p.K == TAB_F64 ? "table_f64" : "table_c64";
     ++*launches;
     return k_begin;
 }
