@@ -285,7 +285,8 @@ def test_segment_split_matches_stream(rng):
 
 @pytest.mark.parametrize("L,ntaps,nch", [(1, 128, 33), (1, 97, 5), (1, 31, 64), (2, 200, 40), (2, 66, 1), (4, 512, 31),
                                           (4, 390, 96)])
-def test_unit_stride_f32_kernel_shapes(L, ntaps, nch, rng):
+@pytest.mark.parametrize("tx", [np.float32, np.complex64])
+def test_unit_stride_f32_kernel_shapes(L, ntaps, nch, tx, rng):
     """The float32 standard / interpolator fast path (mrb_unit.cuh): ragged tap counts (zero-padded tap blocks),
     ragged channel counts (TMA clips rows), chunk lengths that are not whole steps, state carried across
     chunks; against the oracle and the generic kernel."""
@@ -293,10 +294,10 @@ def test_unit_stride_f32_kernel_shapes(L, ntaps, nch, rng):
     h = rng.standard_normal(ntaps).astype(np.float32)
     ratio = Fraction(L, 1)
     n = 5000                                                          # row pitch: a multiple of 16 bytes (TMA)
-    x = rand_samples(rng, (nch, n), np.float32)
+    x = rand_samples(rng, (nch, n), tx)
     xd = torch.from_numpy(x).cuda()
     f = mr.FIRFilter(h, ratio)
-    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=np.float32)
+    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
     g.set_kernel_policy(1)
     o = mo.FIRFilter(h, ratio)
     for a, b in ((0, 2048), (2048, 2052), (2052, 4001), (4001, 4008), (4008, n)):   # 4001: misaligned -> generic
@@ -308,7 +309,9 @@ def test_unit_stride_f32_kernel_shapes(L, ntaps, nch, rng):
         assert y.shape == (nch, (b - a) * L)
         assert nerr(y[: min(nch, 3)], w) <= 1e-5
         assert nerr(yg.cpu().numpy(), y) <= 2e-6
-    assert f.last_kernel.startswith("unit_f32"), f.last_kernel
+    # complex64 with <= 24 taps and L = 1 is the tiled kernel's; everything else here is the unit kernel's
+    want = "tiled" if (tx == np.complex64 and L == 1 and ntaps <= 24) else ("unit_c64" if tx == np.complex64 else "unit_f32")
+    assert f.last_kernel.startswith(want), f.last_kernel
 
 
 @pytest.mark.parametrize("M,ntaps,nch", [(8, 256, 33), (8, 100, 5), (8, 7, 64), (4, 128, 40), (4, 33, 1), (2, 64, 31),
@@ -428,6 +431,9 @@ def test_fast_paths_random_stress_against_generic_kernel(rng):
     for _ in range(4):                                             # unit: float32, L in {1, 2, 4}
         L = int(r.choice([1, 2, 4]))
         cases.append((Fraction(L, 1), int(r.integers(1, 128 * L + 1)), np.float32, "unit"))
+    for _ in range(4):                                             # unit: complex64, more than 24 taps per phase
+        L = int(r.choice([1, 2, 4]))
+        cases.append((Fraction(L, 1), int(r.integers(24 * L + 1, 128 * L + 1)), np.complex64, "unit_c64"))
     for _ in range(4):                                             # decimator: complex64, M in {2, 4, 8}
         M = int(r.choice([2, 4, 8]))
         cases.append((Fraction(1, M), int(r.integers(1, 32 * M + 1)), np.complex64, "decim"))
