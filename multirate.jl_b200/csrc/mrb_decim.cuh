@@ -1,4 +1,4 @@
-// mrb_decim.cuh -- fast path for FIRDecimator (src/Filters.jl:598-631) on complex64 samples x float32 taps
+// mrb_decim.cuh -- fast path for FIRDecimator (src/Filters.jl:598-631) on complex64 or float32 samples x float32 taps
 // (BASELINE configs[1]: 1//8, 256 taps, 1024 channels, streamed 64K-sample chunks).
 //
 // y[k] = sum_i hflip[i] x[kM + i + e]: every output needs M new samples and T old ones, so a lane-per-channel
@@ -30,19 +30,21 @@ struct alignas(16) DecParams {
     long long k_begin, N;      // this launch covers outputs [k_begin, N)
     long long e;               // x index of the first sample of output 0's (padded) window
     int KT;                    // outputs per tile (multiple of M)
-    int delta;                 // which tap table: TMA box starts must be 16-byte aligned, i.e. on an even sample, so
-                               // the padded window starts at e (even) and the taps are placed delta slots later
+    int delta;                 // which tap table: TMA box starts must be 16-byte aligned (an even complex64 sample, a
+                               // float32 sample index that is a multiple of 4), so the padded window starts at an
+                               // aligned e and the taps are placed delta slots later
     const float *taps;         // device: taps[delta][j * 32 + q] = padded hflip[j*M + q] (tap-major: a warp's loads of
                                // one slot touch M consecutive floats)
 };
 
-template <int M>
+template <int M, bool CPLX>
 struct DecCfg {
+    static constexpr int ES = CPLX ? 8 : 4;                         // bytes per sample
     static constexpr int G = 8 / M;                                 // groups of M outputs per lane per step (R = 8)
     static constexpr int R = G * M;                                 // outputs per channel per step
     static constexpr int CPW = 32 / M;                              // channels per warp
     static constexpr int WARPS = kDecRows / CPW;                    // warps per CTA (32 channels)
-    static constexpr int ROW_BYTES = kDecRows * M * 8;              // one decimated index, all channels
+    static constexpr int ROW_BYTES = kDecRows * M * ES;             // one decimated index, all channels
     static constexpr int LIVE = R + kDecTQ - 1;                     // rows a step reads
     static constexpr int LIVE_SLOTS = (LIVE + R - 1) / R;           // ... in units of R rows (one mbarrier each)
     static constexpr int NSLOT = LIVE_SLOTS + 2;                    // ring: live + two steps ahead
@@ -50,11 +52,11 @@ struct DecCfg {
     static constexpr int SMEM = NROW * ROW_BYTES + 8 * NSLOT;
 };
 
-template <int M>
-__global__ void __launch_bounds__(32 * DecCfg<M>::WARPS, 2)
-k_decim_c64(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, long long ldy, int nch,
-            const __grid_constant__ DecParams P) {
-    using C = DecCfg<M>;
+template <int M, bool CPLX>
+__global__ void __launch_bounds__(32 * DecCfg<M, CPLX>::WARPS, 2)
+k_decim(const __grid_constant__ CUtensorMap tmx, void *__restrict__ yv, long long ldy, int nch,
+        const __grid_constant__ DecParams P) {
+    using C = DecCfg<M, CPLX>;
     constexpr int R = C::R, NSLOT = C::NSLOT;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + C::NROW * C::ROW_BYTES);
@@ -66,7 +68,7 @@ k_decim_c64(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, lon
     const int cl = warp * C::CPW + lane / M;                         // channel within the CTA
     const int ch0 = blockIdx.y * kDecRows;
     const uint32_t in_base = smem_u32(smem), bar_base = smem_u32(bars);
-    const uint32_t lanepart = (uint32_t)(cl * M + q) * 8u;           // this lane's sample inside a row
+    const uint32_t lanepart = (uint32_t)(cl * M + q) * (uint32_t)C::ES;   // this lane's sample inside a row
 
     const long long k0 = P.k_begin + (long long)blockIdx.x * P.KT;   // first output of the tile
     const int ntile = (int)min((long long)P.KT, P.N - k0);
@@ -85,7 +87,7 @@ k_decim_c64(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, lon
         mbar_expect_tx(bar, R * C::ROW_BYTES);
         for (int r = 0; r < R; ++r)
             tma_load_2d(in_base + (uint32_t)((slot * R + r) * C::ROW_BYTES), &tmx,
-                        (int)((x0 + ((long long)g * R + r) * M) * 2), ch0, bar);
+                        (int)((x0 + ((long long)g * R + r) * M) * (CPLX ? 2 : 1)), ch0, bar);
     };
     if (tid == 0) {
         for (int i = 0; i < NSLOT; ++i) mbar_init(bar_base + 8 * i, 1);
@@ -112,7 +114,12 @@ k_decim_c64(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, lon
 #pragma unroll
             for (int m = 0; m < C::LIVE; ++m) {
                 const uint32_t a = in_base + (uint32_t)(row * C::ROW_BYTES) + lanepart;
-                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w[m].x), "=f"(w[m].y) : "r"(a) : "memory");
+                if constexpr (CPLX) {
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w[m].x), "=f"(w[m].y) : "r"(a) : "memory");
+                } else {
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[m].x) : "r"(a) : "memory");
+                    w[m].y = 0.f;
+                }
                 if (++row == C::NROW) row = 0;
             }
         }
@@ -124,7 +131,7 @@ k_decim_c64(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, lon
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 acc[r].x = fmaf(t[j], w[r + j].x, acc[r].x);
-                acc[r].y = fmaf(t[j], w[r + j].y, acc[r].y);
+                if constexpr (CPLX) acc[r].y = fmaf(t[j], w[r + j].y, acc[r].y);
             }
         }
         // ---- reduce-scatter over the M residue lanes, one group of M outputs at a time: afterwards lane q holds
@@ -138,15 +145,18 @@ k_decim_c64(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, lon
                 for (int i = 0; i < h; ++i) {
                     const float2 keep = up ? acc[g * M + i + h] : acc[g * M + i];
                     const float2 send = up ? acc[g * M + i] : acc[g * M + i + h];
-                    float2 got;
+                    float2 got = make_float2(0.f, 0.f);
                     got.x = __shfl_xor_sync(0xffffffffu, send.x, h);
-                    got.y = __shfl_xor_sync(0xffffffffu, send.y, h);
+                    if constexpr (CPLX) got.y = __shfl_xor_sync(0xffffffffu, send.y, h);
                     acc[g * M + i] = make_float2(keep.x + got.x, keep.y + got.y);
                 }
             }
             const long long k = k0 + (long long)s * R + g * M + q;
             const int c = ch0 + cl;
-            if (k < P.N && c < nch) y[(long long)c * ldy + k] = acc[g * M];
+            if (k < P.N && c < nch) {
+                if constexpr (CPLX) static_cast<float2 *>(yv)[(long long)c * ldy + k] = acc[g * M];
+                else static_cast<float *>(yv)[(long long)c * ldy + k] = acc[g * M].x;
+            }
         }
 
         // ---- every warp is done with the rows before the next step's window: refill them
@@ -175,6 +185,7 @@ k_decim_c64(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, lon
 // ---------------------------------------------------------------------------------------------------------
 struct DecPlan {
     bool ok = false;
+    bool cplx = true;                  // complex64 samples, else float32
     int M = 8;
     int64_t T = 0;
     DecParams *hp = nullptr;
@@ -195,8 +206,10 @@ static inline void decim_release(DecPlan &p) {
 static inline int32_t decim_prepare(DecPlan &p, int kind, int tx, int ty, int64_t L, int64_t M, int64_t T,
                                     const std::vector<double> &bank, const cudaDeviceProp &prop) {
     p.ok = false;
-    if (kind != 2 || tx != 2 || ty != 2 || L != 1) return 0;
-    if (!(M == 2 || M == 4 || M == 8) || T > (kDecTQ - 1) * M) return 0;
+    if (kind != 2 || tx != ty || !(tx == 2 || tx == 0) || L != 1) return 0;
+    p.cplx = tx == 2;
+    // float32: a TMA box row is M*4 bytes (>= 16) and the window start is aligned to 4 samples (M >= 4)
+    if (!((p.cplx && M == 2) || M == 4 || M == 8) || T > (kDecTQ - 1) * M) return 0;
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -209,8 +222,9 @@ static inline int32_t decim_prepare(DecPlan &p, int kind, int tx, int ty, int64_
     // padded taps: Tp = 33 M slots; zf zeros in front (they multiply samples older than the window), delta zeros
     // behind (they multiply samples newer than x[n_k]: finite data or TMA zero fill)
     const int64_t Tp = kDecTQ * M;
-    std::vector<float> ht((size_t)2 * kDecTQ * 32, 0.f);
-    for (int64_t delta = 0; delta < 2; ++delta) {
+    const int64_t A = p.cplx ? 2 : 4;                                    // samples per 16 bytes
+    std::vector<float> ht((size_t)A * kDecTQ * 32, 0.f);
+    for (int64_t delta = 0; delta < A; ++delta) {
         const int64_t zf = Tp - T - delta;
         for (int64_t i = 0; i < T; ++i) {
             const int64_t ip = i + zf;
@@ -222,9 +236,14 @@ static inline int32_t decim_prepare(DecPlan &p, int kind, int tx, int ty, int64_
     e = cudaMemcpy(p.d_taps, ht.data(), ht.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return (int32_t)e;
     p.hp->taps = p.d_taps;
-    if (M == 4) e = cudaFuncSetAttribute(k_decim_c64<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<4>::SMEM);
-    else if (M == 8) e = cudaFuncSetAttribute(k_decim_c64<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<8>::SMEM);
-    else e = cudaFuncSetAttribute(k_decim_c64<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<2>::SMEM);
+    if (p.cplx) {
+        if (M == 4) e = cudaFuncSetAttribute(k_decim<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<4, true>::SMEM);
+        else if (M == 8) e = cudaFuncSetAttribute(k_decim<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<8, true>::SMEM);
+        else e = cudaFuncSetAttribute(k_decim<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<2, true>::SMEM);
+    } else {
+        if (M == 4) e = cudaFuncSetAttribute(k_decim<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<4, false>::SMEM);
+        else e = cudaFuncSetAttribute(k_decim<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<8, false>::SMEM);
+    }
     if (e != cudaSuccess) return (int32_t)e;
     p.ok = true;
     return 0;
@@ -238,17 +257,18 @@ static inline int64_t decim_try_launch(DecPlan &p, const GenParams &G, cudaStrea
 #define MRB_DEC_SKIP(why) do { if (trace) fprintf(stderr, "[mrb] decimator kernel not used: %s\n", why); return -1; } while (0)
     if (!p.ok) MRB_DEC_SKIP("configuration not covered");
     if (G.mode != SEQ_INTEGER || G.L != 1 || G.p0 != 0) MRB_DEC_SKIP("not a decimator schedule");
-    if (((uintptr_t)G.x & 15) || ((uintptr_t)G.y & 7) || (G.ldx & 1)) MRB_DEC_SKIP("alignment");
+    const int64_t A = p.cplx ? 2 : 4;
+    if (((uintptr_t)G.x & 15) || ((uintptr_t)G.y & (p.cplx ? 7 : 3)) || (G.ldx % A)) MRB_DEC_SKIP("alignment");
     if (G.n_in >= (1ll << 29) || G.nout >= (1ll << 29)) MRB_DEC_SKIP("size");
     const int M = p.M;
     const int64_t Tp = (int64_t)kDecTQ * M;
     // output k reads x[kM + d0m1 - (T-1) .. kM + d0m1]; with zf = Tp - T - delta zeros in front the padded window
-    // starts at e = d0m1 - (T-1) - zf, and delta makes e even (16-byte aligned TMA box starts)
+    // starts at e = d0m1 - (T-1) - zf, and delta makes e a multiple of A samples (16-byte aligned TMA box starts)
     const int64_t e0 = G.d0m1 - (p.T - 1) - (Tp - p.T);
-    const int64_t delta = ((e0 % 2) + 2) % 2;
+    const int64_t delta = ((-e0 % A) + A) % A;                  // e0 + delta is a multiple of A
     const int64_t e = e0 + delta;
     int64_t k_begin = e >= 0 ? 0 : ceil_div(-e, M);
-    k_begin = (k_begin + M - 1) / M * M;
+    k_begin = (k_begin + 7) / 8 * 8;                           // whole steps: k_begin*M keeps e + k_begin*M aligned
     if (G.nout - k_begin < 64) MRB_DEC_SKIP("chunk too short");
 
     DecParams &P = *p.hp;
@@ -262,9 +282,10 @@ static inline int64_t decim_try_launch(DecPlan &p, const GenParams &G, cudaStrea
     tiles = ceil_div(span, P.KT);
 
     CUtensorMap tmx;
-    cuuint64_t dims[2] = {(cuuint64_t)(2 * G.n_in), (cuuint64_t)G.nch};
-    cuuint64_t strides[1] = {(cuuint64_t)G.ldx * 8};
-    cuuint32_t box[2] = {(cuuint32_t)(2 * M), kDecRows};
+    const int fpe = p.cplx ? 2 : 1;                            // floats per sample
+    cuuint64_t dims[2] = {(cuuint64_t)(fpe * G.n_in), (cuuint64_t)G.nch};
+    cuuint64_t strides[1] = {(cuuint64_t)G.ldx * 4 * fpe};
+    cuuint32_t box[2] = {(cuuint32_t)(fpe * M), kDecRows};
     cuuint32_t es[2] = {1, 1};
     if (p.encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(G.x), dims, strides, box, es,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -272,12 +293,16 @@ static inline int64_t decim_try_launch(DecPlan &p, const GenParams &G, cudaStrea
         MRB_DEC_SKIP("x tensor map");
 #undef MRB_DEC_SKIP
     dim3 grid((unsigned)tiles, (unsigned)groups);
-    float2 *yy = static_cast<float2 *>(G.y);
-    if (M == 4) k_decim_c64<4><<<grid, 32 * DecCfg<4>::WARPS, DecCfg<4>::SMEM, st>>>(tmx, yy, G.ldy, (int)G.nch, P);
-    else if (M == 8) k_decim_c64<8><<<grid, 32 * DecCfg<8>::WARPS, DecCfg<8>::SMEM, st>>>(tmx, yy, G.ldy, (int)G.nch, P);
-    else k_decim_c64<2><<<grid, 32 * DecCfg<2>::WARPS, DecCfg<2>::SMEM, st>>>(tmx, yy, G.ldy, (int)G.nch, P);
+    if (p.cplx) {
+        if (M == 4) k_decim<4, true><<<grid, 32 * DecCfg<4, true>::WARPS, DecCfg<4, true>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
+        else if (M == 8) k_decim<8, true><<<grid, 32 * DecCfg<8, true>::WARPS, DecCfg<8, true>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
+        else k_decim<2, true><<<grid, 32 * DecCfg<2, true>::WARPS, DecCfg<2, true>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
+    } else {
+        if (M == 4) k_decim<4, false><<<grid, 32 * DecCfg<4, false>::WARPS, DecCfg<4, false>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
+        else k_decim<8, false><<<grid, 32 * DecCfg<8, false>::WARPS, DecCfg<8, false>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
+    }
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
-    *name = M == 4 ? "decim_c64_m4" : M == 8 ? "decim_c64_m8" : "decim_c64_m2";
+    *name = p.cplx ? (M == 4 ? "decim_c64_m4" : M == 8 ? "decim_c64_m8" : "decim_c64_m2") : (M == 4 ? "decim_f32_m4" : "decim_f32_m8");
     ++*launches;
     return k_begin;
 }

@@ -316,7 +316,8 @@ def test_unit_stride_f32_kernel_shapes(L, ntaps, nch, tx, rng):
 
 @pytest.mark.parametrize("M,ntaps,nch", [(8, 256, 33), (8, 100, 5), (8, 7, 64), (4, 128, 40), (4, 33, 1), (2, 64, 31),
                                           (2, 19, 96)])
-def test_decimator_c64_kernel_shapes(M, ntaps, nch, rng):
+@pytest.mark.parametrize("tx", [np.complex64, np.float32])
+def test_decimator_c64_kernel_shapes(M, ntaps, nch, tx, rng):
     """The complex64 decimator fast path (mrb_decim.cuh): ragged tap counts, ragged channel counts, chunk
     lengths that leave every possible input deficit behind (so the window start takes every alignment), empty
     outputs; count / state exact, values against the oracle and the generic kernel."""
@@ -324,13 +325,14 @@ def test_decimator_c64_kernel_shapes(M, ntaps, nch, rng):
     h = rng.standard_normal(ntaps).astype(np.float32)
     ratio = Fraction(1, M)
     n = 9000
-    x = rand_samples(rng, (nch, n), np.complex64)
+    x = rand_samples(rng, (nch, n), tx)
     xd = torch.from_numpy(x).cuda()
     f = mr.FIRFilter(h, ratio)
-    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=np.complex64)
+    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
     g.set_kernel_policy(1)
     o = mo.FIRFilter(h, ratio)
-    edges = [0, 3000, 3001, 3003, 6000 + M // 2, 6000 + M // 2 + 2, n]
+    # float32 chunks must start on a multiple of 4 samples for the fast path (16-byte aligned pointers)
+    edges = [0, 3000, 3001, 3003, 6000 + M // 2, 6000 + M // 2 + 2, n] if tx == np.complex64 else [0, 3000, 3004, 3012, 6000 + 4, 6000 + 12, n]
     used = set()
     for a, b in zip(edges[:-1], edges[1:]):
         yd = f.filt(xd[:, a:b])
@@ -343,7 +345,8 @@ def test_decimator_c64_kernel_shapes(M, ntaps, nch, rng):
         assert nerr(yg.cpu().numpy(), y) <= 2e-6
         assert states_equal(f, o)
         used.add(f.last_kernel)
-    assert any(k.startswith("decim_c64") for k in used), used
+    if tx == np.complex64 or M >= 4:                                # float32 needs M >= 4 (16-byte TMA rows)
+        assert any(k.startswith("decim_c64" if tx == np.complex64 else "decim_f32") for k in used), used
 
 
 @pytest.mark.parametrize("tx", [np.float32, np.float64, np.complex64])
@@ -437,6 +440,9 @@ def test_fast_paths_random_stress_against_generic_kernel(rng):
     for _ in range(4):                                             # decimator: complex64, M in {2, 4, 8}
         M = int(r.choice([2, 4, 8]))
         cases.append((Fraction(1, M), int(r.integers(1, 32 * M + 1)), np.complex64, "decim"))
+    for _ in range(3):                                             # decimator: float32, M in {4, 8}
+        M = int(r.choice([4, 8]))
+        cases.append((Fraction(1, M), int(r.integers(1, 32 * M + 1)), np.float32, "decim_f32"))
     for ratio, ntaps, tx, want in cases:
         h = r.standard_normal(ntaps).astype(np.float32)
         nch = int(r.integers(1, 200))
