@@ -61,7 +61,7 @@ struct alignas(16) TiledParams {
     long long k_begin, N;      // this launch covers outputs [k_begin, N)
     int L, M;
     int KT;                    // outputs per tile (multiple of 16)
-    int dbg;                   // development switches (MRB_TILED_DBG); 0 in production
+    int pad0;
     // Start state of every time tile, computed on the host (closed form of src/Filters.jl:567-568) so that the
     // kernel's sequencing starts from parameter space and stays in the uniform datapath.
     //   j   : bank row of the tile's first output (rows are stored in RUN ORDER, see `bank`)
@@ -294,7 +294,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
             // (q_flushed = chunk of the previous run's first output).  Two runs span <= 7 + 2*RMAX = 31 outputs from
             // the start of chunk q_flushed, i.e. at most 4 chunks: with 4 buffers the two sets never share a
             // buffer, and everything older was confirmed by the wait above.
-            if (flush && !(P.dbg & 4)) {
+            if (flush) {
 #pragma unroll 1
                 for (int q = q_flushed; q < q_done; ++q) {
                     tma_store_2d(&tmy, yc0 + q * 16, ch0, out_base + (uint32_t)((q & (kOutBufs - 1)) * kOutBytes));
@@ -310,7 +310,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 
         // both halves run the same code (their windows were loaded RW samples apart): first row / output / count of
         // this warp's part of the run are uniform values, not template parameters -- half the instruction footprint
-        if (len > half * RW && !(P.dbg & 8)) {
+        if (len > half * RW) {
             const int r0 = half * RW;
             if (s & 1) run_body<TPAD, RW, 1, OB>(P, xw, rowpart, j + r0, len - r0, k + r0, out_base);
             else run_body<TPAD, RW, 0, OB>(P, xw, rowpart, j + r0, len - r0, k + r0, out_base);
@@ -392,7 +392,6 @@ static inline int32_t tiled_prepare(TiledPlan &p, int kind, int tx, int ty, int6
     p.hp = new TiledParams();
     memset(p.hp, 0, sizeof(TiledParams));
     p.hp->L = (int)L; p.hp->M = (int)M;
-    if (const char *ev = getenv("MRB_TILED_DBG")) p.hp->dbg = atoi(ev);
     if (const char *ev = getenv("MRB_TILED_KT")) { p.kt_min = std::max(64, atoi(ev) / 16 * 16); p.kt_forced = true; }
     // shared-memory address words (see load_window / run_body)
     for (int c = 0; c < 4; ++c)
