@@ -87,6 +87,7 @@ struct mrb_filter {
     void *d_xs = nullptr, *d_ys = nullptr;
     size_t xs_bytes = 0, ys_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};   // further streams of the mrb_filt_host pipeline
     // table kinds: the schedule of the call in flight.  The exact replay costs ~0.3 ms per 60 K outputs, and a caller
     // typically asks for the count (to size its buffer) right before it filters: the last replay is cached, keyed by
     // the state it started from and the input length.
@@ -124,6 +125,7 @@ static void free_device(mrb_filter *f) {
     table_release(f->table);
     for (auto &p : f->tev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (f->own_stream) cudaStreamDestroy(f->own_stream);
+    for (auto &hs : f->host_streams) if (hs) cudaStreamDestroy(hs);
 }
 
 // src/Filters.jl:284-298, written phase-major: bank[phi*T + (T-1-r)] = h[r*Nphi + phi]
@@ -693,11 +695,10 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
     const size_t xb = (size_t)cb * lxs * es, yb = (size_t)cb * lys * eo;
     rc = grow(&f->d_xs, &f->xs_bytes, nst * xb); if (rc) return rc;
     rc = grow(&f->d_ys, &f->ys_bytes, nst * yb); if (rc) return rc;
-    static thread_local cudaStream_t extra[3] = {nullptr, nullptr, nullptr};
     cudaStream_t sts[4] = {f->own_stream, nullptr, nullptr, nullptr};
-    for (int i = 1; i < nst; ++i) {
-        if (!extra[i - 1]) CU(cudaStreamCreateWithFlags(&extra[i - 1], cudaStreamNonBlocking));
-        sts[i] = extra[i - 1];
+    for (int i = 1; i < nst; ++i) {                        // the handle's own streams, on the handle's device
+        if (!f->host_streams[i - 1]) CU(cudaStreamCreateWithFlags(&f->host_streams[i - 1], cudaStreamNonBlocking));
+        sts[i] = f->host_streams[i - 1];
     }
     int b = 0;
     for (int64_t c0 = 0; c0 < f->nch; c0 += cb, b = (b + 1) % nst) {
@@ -707,6 +708,8 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
         if (n_in > 0)
             CU(cudaMemcpy2DAsync(dx, (size_t)lxs * es, static_cast<const char *>(x) + (size_t)(c0 * ldx) * es,
                                  (size_t)ldx * es, (size_t)n_in * es, (size_t)nc, cudaMemcpyHostToDevice, st));
+        // (arbitrary / farrow: every block re-uploads the same schedule slices and rebuilds the same tap rows into the
+        // handle's buffers; blocks on other streams may be reading them meanwhile, but the bytes are identical)
         rc = run_channels(f, dx, lxs, n_in, dy, lys, N, c0, nc, st);
         if (rc) return rc;
         if (N > 0)
