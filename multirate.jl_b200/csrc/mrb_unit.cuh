@@ -92,39 +92,62 @@ k_unit_f32(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUte
     uint32_t w_par = 0;
 
     for (int s = 0; s < nsteps; ++s) {
-        float acc[L][R];
+        // Two consecutive inputs of a phase share their taps, so they are accumulated as one packed pair (FFMA2 with the
+        // tap as a uniform scalar operand): half the issue slots of FFMA -- the path is issue bound.  Inputs (r, r+1)
+        // and tap j read window samples (1+r+j, 2+r+j), which is an aligned register pair only when r + j is odd.  Odd
+        // taps therefore accumulate into pairs (0,1), (2,3), ... (accA) and even taps into pairs (-1,0), (1,2), ...,
+        // (R-1,R) (accB, its two outer halves unused); the two sets meet once per step.
+        unsigned long long accA[L][R / 2], accB[L][R / 2 + 1];
 #pragma unroll
-        for (int ph = 0; ph < L; ++ph)
+        for (int ph = 0; ph < L; ++ph) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[ph][r] = 0.f;
+            for (int r = 0; r < R / 2; ++r) accA[ph][r] = 0ull;
+#pragma unroll
+            for (int r = 0; r <= R / 2; ++r) accB[ph][r] = 0ull;
+        }
 
         for (int bb = 0; bb < P.nblk; ++bb) {
             // window of this warp for tap block bb: tile-relative samples [u0, u0 + R + 32)
             const int u0 = s * C::IS + warp * R + bb * kUnitTB;
             const int need = (u0 + R + kUnitTB - 1) >> 5;
+#pragma unroll 1
             for (; j_waited <= need; ++j_waited) {
                 mbar_wait(bar_base + 8 * w_slot, w_par);
                 if (++w_slot == NB) { w_slot = 0; w_par ^= 1u; }
             }
-            float w[4 * NQ];
+            unsigned long long w2[2 * NQ];                           // w2[i] = window samples (2i, 2i+1)
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 const int u = u0 + 4 * q;
                 const uint32_t word = (uint32_t)(((u >> 2) & 7) << 4) + (uint32_t)(((u >> 5) % NB) * kUnitBoxBytes);
                 const uint32_t a = in_base + (rowpart ^ word);
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(w[4 * q]), "=f"(w[4 * q + 1]), "=f"(w[4 * q + 2]), "=f"(w[4 * q + 3]) : "r"(a) : "memory");
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w2[2 * q]), "=l"(w2[2 * q + 1]) : "r"(a) : "memory");
             }
-            // tap j of the block multiplies, for input r of this warp, window sample 1 + r + j
 #pragma unroll
             for (int ph = 0; ph < L; ++ph) {
                 const float *taps = P.bank + (ph * P.nblk + bb) * kUnitTB;
 #pragma unroll
-                for (int j = 0; j < kUnitTB; ++j) {
-                    const float t = taps[j];
+                for (int j = 0; j < kUnitTB; j += 2) {
+                    const float te = taps[j], to = taps[j + 1];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) acc[ph][r] = fmaf(t, w[1 + r + j], acc[ph][r]);
+                    for (int b = 0; b <= R / 2; ++b) cfma(accB[ph][b], te, w2[b + j / 2]);        // inputs (2b-1, 2b)
+#pragma unroll
+                    for (int b = 0; b < R / 2; ++b) cfma(accA[ph][b], to, w2[b + j / 2 + 1]);     // inputs (2b, 2b+1)
                 }
+            }
+        }
+        float acc[L][R];
+#pragma unroll
+        for (int ph = 0; ph < L; ++ph) {
+            float blo[R / 2 + 1], bhi[R / 2 + 1];
+#pragma unroll
+            for (int b = 0; b <= R / 2; ++b) asm("mov.b64 {%0, %1}, %2;" : "=f"(blo[b]), "=f"(bhi[b]) : "l"(accB[ph][b]));
+#pragma unroll
+            for (int b = 0; b < R / 2; ++b) {
+                float alo, ahi;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(alo), "=f"(ahi) : "l"(accA[ph][b]));
+                acc[ph][2 * b] = alo + bhi[b];
+                acc[ph][2 * b + 1] = ahi + blo[b + 1];
             }
         }
 
