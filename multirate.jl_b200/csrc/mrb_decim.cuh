@@ -108,30 +108,62 @@ k_decim(const __grid_constant__ CUtensorMap tmx, void *__restrict__ yv, long lon
             mbar_wait(bar_base + 8 * w_slot, w_par);
             if (++w_slot == NSLOT) { w_slot = 0; w_par ^= 1u; }
         }
-        float2 w[C::LIVE];
+        // complex samples travel as packed (re, im) pairs: one FFMA2 per tap with the lane's tap as its scalar operand
+        unsigned long long w2[CPLX ? C::LIVE : 1];
+        float w1[CPLX ? 1 : C::LIVE];
         {
             int row = (s % NSLOT) * R;
 #pragma unroll
             for (int m = 0; m < C::LIVE; ++m) {
                 const uint32_t a = in_base + (uint32_t)(row * C::ROW_BYTES) + lanepart;
-                if constexpr (CPLX) {
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w[m].x), "=f"(w[m].y) : "r"(a) : "memory");
-                } else {
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w[m].x) : "r"(a) : "memory");
-                    w[m].y = 0.f;
-                }
+                if constexpr (CPLX) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w2[m]) : "r"(a) : "memory");
+                else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w1[m]) : "r"(a) : "memory");
                 if (++row == C::NROW) row = 0;
             }
         }
         float2 acc[R];
+        if constexpr (CPLX) {
+            unsigned long long a2[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+            for (int r = 0; r < R; ++r) a2[r] = 0ull;
 #pragma unroll
-        for (int j = 0; j < kDecTQ; ++j) {
+            for (int j = 0; j < kDecTQ; ++j) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                acc[r].x = fmaf(t[j], w[r + j].x, acc[r].x);
-                if constexpr (CPLX) acc[r].y = fmaf(t[j], w[r + j].y, acc[r].y);
+                for (int r = 0; r < R; ++r) cfma(a2[r], t[j], w2[r + j]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[r].x), "=f"(acc[r].y) : "l"(a2[r]));
+        } else {
+            // real samples: two consecutive outputs share a tap and read consecutive window samples (r + j, r + j + 1),
+            // an aligned register pair when r + j is even.  Even taps accumulate into output pairs (0,1) .. (6,7), odd
+            // taps into pairs (-1,0), (1,2) .. (7,8) (outer halves unused); the two sets are added once per step.
+            static_assert(R == 8 && (C::LIVE % 2) == 0, "pairing below assumes 8 outputs per step");
+            unsigned long long wp[C::LIVE / 2], aA[R / 2], aB[R / 2 + 1];
+#pragma unroll
+            for (int i = 0; i < C::LIVE / 2; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(wp[i]) : "f"(w1[2 * i]), "f"(w1[2 * i + 1]));
+#pragma unroll
+            for (int b = 0; b < R / 2; ++b) aA[b] = 0ull;
+#pragma unroll
+            for (int b = 0; b <= R / 2; ++b) aB[b] = 0ull;
+#pragma unroll
+            for (int j = 0; j < kDecTQ; ++j) {
+                if (j % 2 == 0) {
+#pragma unroll
+                    for (int b = 0; b < R / 2; ++b) cfma(aA[b], t[j], wp[b + j / 2]);            // outputs (2b, 2b+1)
+                } else {
+#pragma unroll
+                    for (int b = 0; b <= R / 2; ++b) cfma(aB[b], t[j], wp[b + (j - 1) / 2]);     // outputs (2b-1, 2b)
+                }
+            }
+            float blo[R / 2 + 1], bhi[R / 2 + 1];
+#pragma unroll
+            for (int b = 0; b <= R / 2; ++b) asm("mov.b64 {%0, %1}, %2;" : "=f"(blo[b]), "=f"(bhi[b]) : "l"(aB[b]));
+#pragma unroll
+            for (int b = 0; b < R / 2; ++b) {
+                float alo, ahi;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(alo), "=f"(ahi) : "l"(aA[b]));
+                acc[2 * b] = make_float2(alo + bhi[b], 0.f);
+                acc[2 * b + 1] = make_float2(ahi + blo[b + 1], 0.f);
             }
         }
         // ---- reduce-scatter over the M residue lanes, one group of M outputs at a time: afterwards lane q holds
