@@ -100,6 +100,7 @@ struct mrb_filter {
     DecPlan decim;                     // fast path for complex64 decimators (mrb_decim.cuh)
     TabPlan table;                     // fast path for arbitrary / farrow on real samples (mrb_table.cuh)
     int policy = 0;
+    int num_sms = 148;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // one pair per timed mrb_filt
     const char *last_kernel = "none";
@@ -224,6 +225,7 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
         if (prop.major != 10)
             return fail(MRB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library holds sm_100a code only", f->device,
                         prop.major, prop.minor);
+        f->num_sms = prop.multiProcessorCount;
         const bool dbl = is_double(f->ty);
         CU(dbl ? upload_real<double>(f->bank, &f->d_bank) : upload_real<float>(f->bank, &f->d_bank));
         if (kind == MRB_ARBITRARY) CU(dbl ? upload_real<double>(f->dbank, &f->d_dbank) : upload_real<float>(f->dbank, &f->d_dbank));
@@ -496,8 +498,47 @@ static void launch_generic(const GenParams &P, cudaStream_t st) {
     k_generic<RX, R, NC><<<grid, 256, 0, st>>>(P);
 }
 
-static void dispatch_generic(const mrb_filter *f, const GenParams &P, cudaStream_t st) {
+// k_stream: integer schedules with enough outputs to pay for staging the bank once per CTA
+constexpr int64_t kStreamMinOutputs = 8192;
+constexpr int64_t kStreamMaxBankBytes = 96 * 1024;
+
+template <typename RX, typename R, int NC>
+static bool launch_stream(const GenParams &P, int num_sms, int device, cudaStream_t st) {
+    const int64_t pitch = P.T | 1;                                     // odd row pitch: 32 branches -> 32 banks
+    const int64_t bytes = P.L * pitch * (int64_t)sizeof(R);
+    if (P.mode != SEQ_INTEGER || P.nout < kStreamMinOutputs || bytes > kStreamMaxBankBytes || P.L >= (1ll << 31) / pitch)
+        return false;
+    static bool attr_set[64] = {};                                     // per instantiation and device
+    if (device < 0 || device >= 64) return false;
+    if (!attr_set[device]) {
+        if (cudaFuncSetAttribute(k_stream<RX, R, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamMaxBankBytes) != cudaSuccess)
+            return false;
+        attr_set[device] = true;
+    }
+    const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(8, (200 * 1024) / (bytes + 1024)));
+    const int64_t target = per_sm * num_sms;
+    const int64_t gx = std::min<int64_t>(ceil_div(P.nout, 256), target);
+    const int64_t gy = std::min<int64_t>(P.nch, std::max<int64_t>(1, target / gx));
+    k_stream<RX, R, NC><<<dim3((unsigned)gx, (unsigned)gy), 256, (size_t)bytes, st>>>(P, (int)pitch);
+    return true;
+}
+
+// Returns the name of the kernel that was launched.  policy != 0 (MRB_POLICY_GENERIC) keeps to k_generic.
+static const char *dispatch_generic(const mrb_filter *f, const GenParams &P, cudaStream_t st) {
     const int key = f->tx * 4 + f->ty;
+    const int sms = f->num_sms;
+    if (f->policy == 0) {
+        bool done = false;
+        switch (key) {
+        case MRB_F32 * 4 + MRB_F32: done = launch_stream<float, float, 1>(P, sms, f->device, st); break;
+        case MRB_C64 * 4 + MRB_C64: done = launch_stream<float, float, 2>(P, sms, f->device, st); break;
+        case MRB_F32 * 4 + MRB_F64: done = launch_stream<float, double, 1>(P, sms, f->device, st); break;
+        case MRB_C64 * 4 + MRB_C128: done = launch_stream<float, double, 2>(P, sms, f->device, st); break;
+        case MRB_F64 * 4 + MRB_F64: done = launch_stream<double, double, 1>(P, sms, f->device, st); break;
+        case MRB_C128 * 4 + MRB_C128: done = launch_stream<double, double, 2>(P, sms, f->device, st); break;
+        }
+        if (done) return "stream";
+    }
     switch (key) {
     case MRB_F32 * 4 + MRB_F32: launch_generic<float, float, 1>(P, st); break;
     case MRB_C64 * 4 + MRB_C64: launch_generic<float, float, 2>(P, st); break;
@@ -506,6 +547,7 @@ static void dispatch_generic(const mrb_filter *f, const GenParams &P, cudaStream
     case MRB_F64 * 4 + MRB_F64: launch_generic<double, double, 1>(P, st); break;
     case MRB_C128 * 4 + MRB_C128: launch_generic<double, double, 2>(P, st); break;
     }
+    return "generic";
 }
 
 static void launch_history(const mrb_filter *f, const void *x, int64_t ldx, int64_t n_in, const void *hold, void *hnew,
@@ -564,8 +606,9 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 if (k_begin == -2) return fail(MRB_ERR_CUDA, "fast-path launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
             if (k_begin != 0) {            // generic kernel: everything, or the head the tiled kernel left out
-                if (k_begin > 0) P.nout = k_begin; else f->last_kernel = "generic";
-                dispatch_generic(f, P, st);
+                if (k_begin > 0) P.nout = k_begin;
+                const char *gname = dispatch_generic(f, P, st);
+                if (k_begin < 0) f->last_kernel = gname;
                 ++f->launches;
             }
         } else {

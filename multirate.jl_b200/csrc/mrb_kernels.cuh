@@ -1,5 +1,6 @@
 // mrb_kernels.cuh -- generic (any kind, any dtype, any alignment) sm_100a kernels:
 //   k_generic      one thread per output sample, loops over its channel slice
+//   k_stream       the same for integer schedules, polyphase bank staged in shared memory
 //   k_farrow_taps  per-output Farrow tap rows (Float64 Horner, rounded to the tap type)
 //   k_history      history carry  hist <- last H of [hist | x]   (shiftin!, src/support.jl:61-80)
 // The tiled fast paths live in mrb_tiled.cuh; this file is the always-correct path that
@@ -76,8 +77,16 @@ __global__ void __launch_bounds__(256) k_generic(const GenParams P) {
     double alpha = 0.0;
     if (P.mode == SEQ_INTEGER) {
         const int64_t t = P.p0 + k * P.M;
-        n = P.d0m1 + t / P.L;
-        taps = static_cast<const R *>(P.bank) + (t % P.L) * P.T;
+        int64_t tq, tr;
+        if ((uint64_t)t < (1ull << 32) && (uint64_t)P.L < (1ull << 32)) {   // the usual case: one 32-bit division
+            tq = (uint32_t)t / (uint32_t)P.L;
+            tr = (uint32_t)t - (uint32_t)tq * (uint32_t)P.L;
+        } else {
+            tq = t / P.L;
+            tr = t - tq * P.L;
+        }
+        n = P.d0m1 + tq;
+        taps = static_cast<const R *>(P.bank) + tr * P.T;
     } else if (P.mode == SEQ_ARBITRARY) {
         n = P.sn[kl];
         const int64_t phi = P.sphi[kl];
@@ -88,17 +97,18 @@ __global__ void __launch_bounds__(256) k_generic(const GenParams P) {
         n = P.sn[kl];
         taps = static_cast<const R *>(P.taptab) + kl * P.T;
     }
-    const int64_t T = P.T, H = P.H;
+    const int64_t H = P.H;
+    const int T = (int)P.T;
     // taps i in [0, ih) read history, [ih, T) read x
-    int64_t ih = H - n;
-    ih = ih < 0 ? 0 : (ih > T ? T : ih);
+    int64_t ihl = H - n;
+    const int ih = (int)(ihl < 0 ? 0 : (ihl > T ? T : ihl));
     for (int64_t c = blockIdx.y; c < P.nch; c += gridDim.y) {
         const RX *__restrict__ xc = static_cast<const RX *>(P.x) + c * P.ldx * NC;
         const RX *__restrict__ hc = static_cast<const RX *>(P.hist) + c * H * NC;
         R acc[NC], dacc[NC];
 #pragma unroll
         for (int q = 0; q < NC; ++q) acc[q] = dacc[q] = R(0);
-        for (int64_t i = 0; i < ih; ++i) {
+        for (int i = 0; i < ih; ++i) {
             RX s[NC];
             ld_sample<RX, NC>(hc, n + i, s);
             const R t = __ldg(taps + i);
@@ -112,7 +122,8 @@ __global__ void __launch_bounds__(256) k_generic(const GenParams P) {
         }
         const RX *__restrict__ xw = xc + (n - H) * NC;
         if (dtaps) {
-            for (int64_t i = ih; i < T; ++i) {
+#pragma unroll 4
+            for (int i = ih; i < T; ++i) {
                 RX s[NC];
                 ld_sample<RX, NC>(xw, i, s);
                 const R t = __ldg(taps + i), dt = __ldg(dtaps + i);
@@ -126,7 +137,8 @@ __global__ void __launch_bounds__(256) k_generic(const GenParams P) {
 #pragma unroll
             for (int q = 0; q < NC; ++q) acc[q] = (R)((double)acc[q] + (double)dacc[q] * alpha);
         } else {
-            for (int64_t i = ih; i < T; ++i) {
+#pragma unroll 4
+            for (int i = ih; i < T; ++i) {
                 RX s[NC];
                 ld_sample<RX, NC>(xw, i, s);
                 const R t = __ldg(taps + i);
@@ -135,6 +147,66 @@ __global__ void __launch_bounds__(256) k_generic(const GenParams P) {
             }
         }
         st_sample<R, NC>(static_cast<R *>(P.y) + c * P.ldy * NC, k, acc);
+    }
+}
+
+// Integer schedules (standard / interpolator / decimator / rational) that no tiled kernel covers -- few channels,
+// Float64, odd alignments: k_generic's thread-per-output mapping, but with the polyphase bank staged in shared memory.
+// Consecutive outputs use different branches (phi advances by M mod L), so a warp's tap loads touch 32 different rows:
+// from global memory that is 32 sectors per request and the L1 data path bounds the kernel (ncu, README benchmark:
+// 18.6 sectors per request, 39 us for 918,750 outputs); from shared memory with an odd row pitch the 32 rows fall
+// into 32 different banks.  Persistent grid-stride CTAs so the bank is staged once per CTA, not once per 256 outputs.
+template <typename RX, typename R, int NC>
+__global__ void __launch_bounds__(256) k_stream(const GenParams P, int pitch) {
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    R *sb = reinterpret_cast<R *>(stream_smem);
+    const int T = (int)P.T;
+    {
+        const R *__restrict__ gb = static_cast<const R *>(P.bank);
+        const int total = (int)P.L * T;
+        for (int idx = threadIdx.x; idx < total; idx += 256) {
+            const int phi = idx / T;
+            sb[phi * pitch + (idx - phi * T)] = __ldg(gb + idx);
+        }
+    }
+    __syncthreads();
+    const int64_t H = P.H;
+    for (int64_t kl = (int64_t)blockIdx.x * 256 + threadIdx.x; kl < P.nout; kl += (int64_t)gridDim.x * 256) {
+        const int64_t k = P.k_base + kl;
+        const int64_t t = P.p0 + k * P.M;
+        int64_t tq, tr;
+        if ((uint64_t)t < (1ull << 32)) {
+            tq = (uint32_t)t / (uint32_t)P.L;
+            tr = (uint32_t)t - (uint32_t)tq * (uint32_t)P.L;
+        } else {
+            tq = t / P.L;
+            tr = t - tq * P.L;
+        }
+        const int64_t n = P.d0m1 + tq;
+        const R *taps = sb + (int)tr * pitch;
+        const int64_t ihl = H - n;
+        const int ih = (int)(ihl < 0 ? 0 : (ihl > T ? T : ihl));
+        for (int64_t c = blockIdx.y; c < P.nch; c += gridDim.y) {
+            const RX *__restrict__ hc = static_cast<const RX *>(P.hist) + c * H * NC;
+            const RX *__restrict__ xw = static_cast<const RX *>(P.x) + (c * P.ldx + (n - H)) * NC;
+            R acc[NC];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) acc[q] = R(0);
+            for (int i = 0; i < ih; ++i) {
+                RX s[NC];
+                ld_sample<RX, NC>(hc, n + i, s);
+#pragma unroll
+                for (int q = 0; q < NC; ++q) acc[q] = fma(taps[i], (R)s[q], acc[q]);
+            }
+#pragma unroll 8
+            for (int i = ih; i < T; ++i) {
+                RX s[NC];
+                ld_sample<RX, NC>(xw, i, s);
+#pragma unroll
+                for (int q = 0; q < NC; ++q) acc[q] = fma(taps[i], (R)s[q], acc[q]);
+            }
+            st_sample<R, NC>(static_cast<R *>(P.y) + c * P.ldy * NC, k, acc);
+        }
     }
 }
 

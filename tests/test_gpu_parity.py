@@ -349,6 +349,45 @@ def test_decimator_c64_kernel_shapes(M, ntaps, nch, tx, rng):
         assert any(k.startswith("decim_c64" if tx == np.complex64 else "decim_f32") for k in used), used
 
 
+@pytest.mark.parametrize("ratio,ntaps", [(Fraction(147, 160), 3528), (Fraction(3, 17), 120), (Fraction(1, 1), 63),
+                                         (Fraction(7, 1), 100), (Fraction(1, 5), 41), (Fraction(160, 147), 1600)])
+@pytest.mark.parametrize("th,tx,nch", [(np.float32, np.float32, 1), (np.float32, np.complex64, 3), (np.float64, np.float64, 2),
+                                       (np.float64, np.complex128, 1), (np.float64, np.float32, 1)])
+def test_stream_kernel_few_channels(ratio, ntaps, th, tx, nch, rng):
+    """k_stream (mrb_kernels.cuh): integer schedules no tiled kernel covers (few channels, Float64, README benchmark
+    shape), polyphase bank staged in shared memory.  Chunks long enough to reach it and short ones that stay on
+    k_generic, odd chunk boundaries, state carried; count / state exact, values against the oracle and k_generic."""
+    import torch
+    h = rng.standard_normal(ntaps).astype(th)
+    big = int(9000 / ratio) + 1                                     # inputs for > 8192 outputs (k_stream's threshold)
+    edges = [0, big, big + 2, big + 499, 2 * big + 499]
+    n = edges[-1]
+    x = rand_samples(rng, (nch, n), tx)
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
+    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
+    g.set_kernel_policy(1)
+    o = mo.FIRFilter(h, ratio)
+    used = set()
+    for a, b in zip(edges[:-1], edges[1:]):
+        yd = f.filt(xd[:, a:b])
+        yg = g.filt(xd[:, a:b])
+        w = o.filt(x[:, a:b])
+        torch.cuda.synchronize()
+        y = yd.cpu().numpy()
+        assert y.shape == w.shape
+        assert nerr(y, w) <= tol_for(y.dtype)
+        assert nerr(yg.cpu().numpy(), y) <= tol_for(y.dtype)
+        assert states_equal(f, o)
+        if y.shape[1] >= 8192:
+            used.add(f.last_kernel)
+        assert g.last_kernel in ("generic", "none")
+    # the long chunks never fall back to k_generic; Float64 work has no other fast path than k_stream
+    assert used and "generic" not in used, used
+    if th == np.float64:
+        assert used == {"stream"}, used
+
+
 @pytest.mark.parametrize("tx", [np.float32, np.float64, np.complex64])
 @pytest.mark.parametrize("polyorder", [None, 4])
 @pytest.mark.parametrize("rate,nch", [(0.918734, 33), (1.37, 64), (1 / 2.123456789, 5)])
