@@ -13,7 +13,8 @@
 // 1/M-th of a warp's shared memory: 16 warps per SM fit.
 //  * rows of M samples per channel arrive by TMA ([32 ch][M samples] boxes, one per decimated index m) in a ring
 //    laid out [row][channel][M samples]: a warp's LDS.64 reads 256 contiguous bytes, conflict free.
-//  * one CTA barrier per step (M outputs per channel = 8 warps x ~600 instructions).
+//  * a ninth warp is the TMA producer; consumer warps hand ring slots back through "empty" mbarriers and never meet
+//    at a CTA barrier, so one warp's window loads (40 LDS per step) overlap another's FMAs.
 // The first outputs of a chunk (window reaches into the history) are computed by k_generic.
 #pragma once
 #include <cstdio>
@@ -49,11 +50,11 @@ struct DecCfg {
     static constexpr int LIVE_SLOTS = (LIVE + R - 1) / R;           // ... in units of R rows (one mbarrier each)
     static constexpr int NSLOT = LIVE_SLOTS + 2;                    // ring: live + two steps ahead
     static constexpr int NROW = NSLOT * R;
-    static constexpr int SMEM = NROW * ROW_BYTES + 8 * NSLOT;
+    static constexpr int SMEM = NROW * ROW_BYTES + 16 * NSLOT;       // + a full and an empty mbarrier per slot
 };
 
 template <int M, bool CPLX>
-__global__ void __launch_bounds__(32 * DecCfg<M, CPLX>::WARPS, 2)
+__global__ void __launch_bounds__(32 * (DecCfg<M, CPLX>::WARPS + 1), 2)
 k_decim(const __grid_constant__ CUtensorMap tmx, void *__restrict__ yv, long long ldy, int nch,
         const __grid_constant__ DecParams P) {
     using C = DecCfg<M, CPLX>;
@@ -76,28 +77,43 @@ k_decim(const __grid_constant__ CUtensorMap tmx, void *__restrict__ yv, long lon
     const long long x0 = P.e + k0 * M;                               // x index of row 0 of the tile (even)
     const int glast = nsteps + (C::LIVE - 1) / R;                    // newest row group (R rows) the tile reads
 
+    // full[slot]: the group's R TMA boxes have landed; empty[slot]: every consumer warp has read the group
+    const uint32_t empty_base = bar_base + 8 * NSLOT;
+    if (tid == 0) {
+        for (int i = 0; i < NSLOT; ++i) {
+            mbar_init(bar_base + 8 * i, 1);
+            mbar_init(empty_base + 8 * i, C::WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
+    }
+    __syncthreads();
+
+    if (warp == C::WARPS) {
+        // ---- producer warp: one mbarrier per group of R rows, a group is R TMA boxes [32 ch][M samples].  It runs
+        // up to NSLOT groups ahead of the slowest consumer warp; the consumer warps never meet at a CTA barrier, so
+        // their window loads and FMA phases overlap.
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t par = 0;                                        // round n >= 1 of a slot waits for phase n-1 of its empty barrier
+            for (int g = 0; g <= glast; ++g) {
+                if (g >= NSLOT) mbar_wait(empty_base + 8 * slot, par);
+                const uint32_t bar = bar_base + 8 * slot;
+                mbar_expect_tx(bar, R * C::ROW_BYTES);
+                for (int r = 0; r < R; ++r)
+                    tma_load_2d(in_base + (uint32_t)((slot * R + r) * C::ROW_BYTES), &tmx,
+                                (int)((x0 + ((long long)g * R + r) * M) * (CPLX ? 2 : 1)), ch0, bar);
+                if (++slot == NSLOT) { slot = 0; if (g >= NSLOT) par ^= 1u; }
+            }
+        }
+        return;
+    }
+
     // this lane's taps: constants for the whole kernel
     float t[kDecTQ];
 #pragma unroll
     for (int j = 0; j < kDecTQ; ++j) t[j] = __ldg(P.taps + (P.delta * kDecTQ + j) * 32 + q);
 
-    // one mbarrier per group of R rows; a group is R TMA boxes [32 ch][M samples]
-    auto issue_group = [&](int g, int slot) {
-        const uint32_t bar = bar_base + 8 * slot;
-        mbar_expect_tx(bar, R * C::ROW_BYTES);
-        for (int r = 0; r < R; ++r)
-            tma_load_2d(in_base + (uint32_t)((slot * R + r) * C::ROW_BYTES), &tmx,
-                        (int)((x0 + ((long long)g * R + r) * M) * (CPLX ? 2 : 1)), ch0, bar);
-    };
-    if (tid == 0) {
-        for (int i = 0; i < NSLOT; ++i) mbar_init(bar_base + 8 * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
-        for (int g = 0; g < NSLOT && g <= glast; ++g) issue_group(g, g);
-    }
-    __syncthreads();
-
-    int g_issued = min(NSLOT, glast + 1), i_slot = g_issued % NSLOT;
     int g_waited = 0, w_slot = 0;
     uint32_t w_par = 0;
 
@@ -191,22 +207,11 @@ k_decim(const __grid_constant__ CUtensorMap tmx, void *__restrict__ yv, long lon
             }
         }
 
-        // ---- every warp is done with the rows before the next step's window: refill them
-        __syncthreads();
-        const int gtarget = min(s + 1 + NSLOT - 1, glast);
-        if (tid == 0) {
-            int sl = i_slot;
-            for (int g = g_issued; g <= gtarget; ++g) {
-                issue_group(g, sl);
-                if (++sl == NSLOT) sl = 0;
-            }
-        }
-        if (gtarget >= g_issued) {
-            i_slot = (i_slot + (gtarget + 1 - g_issued)) % NSLOT;
-            g_issued = gtarget + 1;
-        }
+        // ---- this warp is done with group s (rows below (s+1)R): hand its slot back to the producer
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_base + 8 * (uint32_t)(s % NSLOT)) : "memory");
     }
-    for (; g_waited < g_issued; ++g_waited) {             // every issued load must have landed before exit
+    for (; g_waited <= glast; ++g_waited) {               // every issued load must have landed before exit
         mbar_wait(bar_base + 8 * w_slot, w_par);
         if (++w_slot == NSLOT) { w_slot = 0; w_par ^= 1u; }
     }
@@ -326,12 +331,12 @@ static inline int64_t decim_try_launch(DecPlan &p, const GenParams &G, cudaStrea
 #undef MRB_DEC_SKIP
     dim3 grid((unsigned)tiles, (unsigned)groups);
     if (p.cplx) {
-        if (M == 4) k_decim<4, true><<<grid, 32 * DecCfg<4, true>::WARPS, DecCfg<4, true>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
-        else if (M == 8) k_decim<8, true><<<grid, 32 * DecCfg<8, true>::WARPS, DecCfg<8, true>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
-        else k_decim<2, true><<<grid, 32 * DecCfg<2, true>::WARPS, DecCfg<2, true>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
+        if (M == 4) k_decim<4, true><<<grid, 32 * (DecCfg<4, true>::WARPS + 1), DecCfg<4, true>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
+        else if (M == 8) k_decim<8, true><<<grid, 32 * (DecCfg<8, true>::WARPS + 1), DecCfg<8, true>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
+        else k_decim<2, true><<<grid, 32 * (DecCfg<2, true>::WARPS + 1), DecCfg<2, true>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
     } else {
-        if (M == 4) k_decim<4, false><<<grid, 32 * DecCfg<4, false>::WARPS, DecCfg<4, false>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
-        else k_decim<8, false><<<grid, 32 * DecCfg<8, false>::WARPS, DecCfg<8, false>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
+        if (M == 4) k_decim<4, false><<<grid, 32 * (DecCfg<4, false>::WARPS + 1), DecCfg<4, false>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
+        else k_decim<8, false><<<grid, 32 * (DecCfg<8, false>::WARPS + 1), DecCfg<8, false>::SMEM, st>>>(tmx, G.y, G.ldy, (int)G.nch, P);
     }
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
     *name = p.cplx ? (M == 4 ? "decim_c64_m4" : M == 8 ? "decim_c64_m8" : "decim_c64_m2") : (M == 4 ? "decim_f32_m4" : "decim_f32_m8");
