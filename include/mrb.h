@@ -138,9 +138,11 @@ int32_t mrb_tapsforphase(const mrb_filter *f, double phase, void *taps);
  * which = 0: pfb (or flipped h), 1: dpfb */
 int32_t mrb_get_pfb(const mrb_filter *f, int32_t which, void *dst);
 
-/* Long-stream segment split (no reference counterpart).  Positions the state machine of an
- * integer-ratio filter as if n0 input samples had already been consumed since construction:
- * first output k0 = ceil(n0*L/M), phase (k0*M) mod L, deficit floor(k0*M/L) - n0 + 1; and loads the
+/* Long-stream segment split (no reference counterpart).  Positions the state machine
+ * as if n0 input samples had already been consumed since construction.  Integer ratios: closed form,
+ * first output k0 = ceil(n0*L/M), phase (k0*M) mod L, deficit floor(k0*M/L) - n0 + 1.  Arbitrary / Farrow:
+ * exact host replay of the Float64 phase recurrence (src/Filters.jl:663-673, 780-786) over n0 inputs,
+ * bit-identical to having filtered them (O(outputs) host work, no data touched).  Both load the
  * history from the halo = the history_len samples preceding n0 (device pointer, per channel at
  * halo + c*ld_halo; NULL = zeros).  *k0 receives the absolute index of the segment's first output. */
 int32_t mrb_seek(mrb_filter *f, int64_t n0, const void *halo, int64_t ld_halo, int64_t *k0, void *stream);

@@ -781,11 +781,22 @@ __global__ void k_load_halo(const RX *__restrict__ halo, int64_t ld, RX *__restr
 
 extern "C" int32_t mrb_seek(mrb_filter *f, int64_t n0, const void *halo, int64_t ld_halo, int64_t *k0, void *stream) {
     if (!f || n0 < 0) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
-    if (is_table_kind(f)) return fail(MRB_ERR_UNSUPPORTED, "seek needs the integer schedule (arbitrary-rate start states require a replay)");
-    // state after consuming n0 samples from the constructor state (p=0, d=1): SURVEY 8e
-    const int64_t kk = ceil_div(n0 * f->L, f->M);
-    f->phiIdx = (kk * f->M) % f->L + 1;
-    f->deficit = (kk * f->M) / f->L - n0 + 1;
+    int64_t kk;
+    if (is_table_kind(f)) {
+        // arbitrary / farrow: the Float64 phase recurrence has no closed form that is bit-identical to the reference's
+        // rounding, so the start state is the exact (data independent) replay of n0 inputs from the constructor state
+        // (src/Filters.jl:663-673, 780-786), without storing the schedule: ~2 ns per output on the host.
+        init_state(f);
+        mrb_state e;
+        kk = replay_table(f, n0, &e, nullptr, nullptr, nullptr);
+        commit_state(f, e);
+        f->sched_valid = false;
+    } else {
+        // state after consuming n0 samples from the constructor state (p=0, d=1): SURVEY 8e
+        kk = ceil_div(n0 * f->L, f->M);
+        f->phiIdx = (kk * f->M) % f->L + 1;
+        f->deficit = (kk * f->M) / f->L - n0 + 1;
+    }
     if (k0) *k0 = kk;
     if (f->device >= 0 && f->H > 0) {
         CU(cudaSetDevice(f->device));

@@ -275,6 +275,12 @@ class FIRFilter:
         if nchannels is not None and sample_dtype is not None:
             self._ensure(np.dtype(sample_dtype), int(nchannels))
 
+    def _ctor_args(self):
+        """Positional arguments that rebuild this filter (a probe or a per-segment twin of it)."""
+        if self._ratio is not None:
+            return (self._h, self._ratio)
+        return (self._h, self._rate, self._n_phi) + ((self._polyorder,) if self._kind == _ffi.FARROW else ())
+
     # ---- handle management ------------------------------------------------
     def _ensure(self, tx, nch):
         tx = np.dtype(tx)
@@ -462,6 +468,30 @@ class FIRFilter:
             _ffi.check(_ffi.lib().mrb_reset(self._handle))
         self._pending_state = None
         return self
+
+    def seek(self, n0, halo=None):
+        """Long-stream segment start (no reference counterpart): put the filter in the state it
+        would have after consuming `n0` samples since construction, with `halo` = the historyLen samples preceding n0
+        ([nchannels, historyLen] CUDA tensor, None = zeros) as its history.  Integer ratios use the closed form,
+        arbitrary / Farrow the exact host replay of the phase recurrence.  Returns the absolute index of the segment's
+        first output.  The filter must be bound (nchannels=, sample_dtype= at construction, or a previous filt)."""
+        if self._handle is None or getattr(self, "_host_only", False):
+            if halo is not None:
+                raise ValueError("seek with a halo needs a filter bound to its channels and sample dtype")
+            h = self._host_handle()
+        else:
+            h = self._handle
+        k0 = C.c_int64()
+        ptr, ld, stream = None, max(self.historyLen, 1), None
+        if halo is not None and self.historyLen > 0:
+            import torch
+            if tuple(halo.shape) != (self._nch, self.historyLen) or not halo.is_cuda or not halo.is_contiguous():
+                raise ValueError("halo must be a contiguous CUDA tensor of shape (nchannels, historyLen)")
+            if str(halo.dtype).replace("torch.", "") != str(self._tx):
+                raise TypeError("halo dtype does not match the filter's sample dtype")
+            ptr, stream = halo.data_ptr(), torch.cuda.current_stream(halo.device).cuda_stream
+        _ffi.check(_ffi.lib().mrb_seek(h, int(n0), ptr, ld, C.byref(k0), stream))
+        return k0.value
 
     def setphase(self, phi):
         if not (0 <= phi <= 1):

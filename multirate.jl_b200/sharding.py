@@ -1,6 +1,7 @@
 """Multi-GPU partitioning of the path: channels are independent, so the batch is split into
 contiguous channel blocks, one per GPU, with NO collective on the data path; a single long stream is split into
-input segments that each need only a read-only tap-length halo and a closed-form start state (mrb_seek).
+input segments that each need only a read-only tap-length halo and a start state (mrb_seek: closed form for integer
+ratios, exact phase replay for arbitrary / Farrow).
 Host-side arithmetic only."""
 from __future__ import annotations
 
@@ -27,12 +28,13 @@ def segment_bounds(n_samples: int, world: int, rank: int, align: int = 1):
 
 def segment_plan(filt, n_samples: int, world: int, align: int = 1):
     """[(n0, n1, k0, count)] for every rank: segment bounds, absolute index of its first output, and its output
-    count, from the library's own sequencing (host-only; `filt` must be an integer-ratio FIRFilter)."""
+    count, from the library's own sequencing (host-only).  Integer ratios use the closed-form start state; arbitrary
+    and Farrow filters the exact replay of their phase recurrence, O(n0) host work per segment."""
     from .filters import FIRFilter
     plan = []
     for r in range(world):
         n0, n1 = segment_bounds(n_samples, world, r, align)
-        probe = FIRFilter(filt._h, filt._ratio, nchannels=1, sample_dtype="float32", device=-1)
+        probe = FIRFilter(*filt._ctor_args(), nchannels=1, sample_dtype="float32", device=-1)
         k0, cnt = C.c_int64(), C.c_int64()
         _ffi.check(_ffi.lib().mrb_seek(probe._handle, n0, None, 0, C.byref(k0), None))
         _ffi.check(_ffi.lib().mrb_output_count(probe._handle, n1 - n0, C.byref(cnt)))

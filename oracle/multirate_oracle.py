@@ -437,6 +437,28 @@ class FIRFilter:
             k.currentTaps = polyval(k.pnfb, k.phiIdx).astype(self.th)
         return self
 
+    def setphase(self, phi):
+        """src/Filters.jl:210-232 with the repairs SURVEY section 9 decided (items 1 and 8): the Rational method reads
+        an undefined variable upstream (here phi in [0,1] maps onto branch 1..Nphi); the Arbitrary method upstream can
+        yield branch 0 and leaves the accumulator stale (here the accumulator is set and branch / alpha derive from it);
+        the Farrow method is upstream's (:224-229)."""
+        if not (0 <= phi <= 1):
+            raise AssertionError("phase must be in [0, 1]")
+        k = self.kernel
+        if isinstance(k, FIRRational):
+            k.phiIdx = min(int(math.floor(phi * k.Nphi)) + 1, k.Nphi)
+            return k.phiIdx
+        if isinstance(k, FIRArbitrary):
+            k.phiAccumulator = 1.0 + phi * k.Nphi
+            k.phiIdx = min(int(math.floor(k.phiAccumulator)), k.Nphi)
+            k.alpha = k.phiAccumulator - k.phiIdx
+            return k.phiIdx, k.alpha
+        if isinstance(k, FIRFarrow):
+            k.phiIdx = phi * (k.Nphi - 1) + 1                                       # :226
+            k.currentTaps = tapsforphase_farrow(k, k.phiIdx)                        # :227
+            return k.phiIdx
+        raise ValueError("setphase is not supported for this kernel (it carries no phase)")
+
     def state(self):
         """(phase index 1-based, inputDeficit, accumulator, alpha) for state read-back tests."""
         k = self.kernel

@@ -283,6 +283,70 @@ def test_segment_split_matches_stream(rng):
     assert (got - whole).abs().max().item() <= 1e-6 * whole.abs().max().item()
 
 
+@pytest.mark.parametrize("case", ["farrow", "arbitrary", "rational"])
+def test_output_time_offset_api(case, rng):
+    """the documented use of setphase (examples/FIRFarrow.jl:25-30) -- throw away whole samples by
+    raising kernel.inputDeficit, set the fractional phase with setphase, then filt -- against the oracle with the same
+    two pokes: count, state and values; then a second chunk continues from the carried state."""
+    N, tpp = 32, 10
+    h = (mo.firdes(tpp * N, 0.45 / N, 5.6533) * N)
+    if case == "farrow":
+        args = (h, 1.1234, N, 4)
+    elif case == "arbitrary":
+        args = (h, 1.1234, N)
+    else:
+        args = (h[:96], Fraction(7, 5))
+    x = rand_samples(rng, (2, 5000), np.float64)
+    delay = (len(args[0]) - 1) / (2 * N) + 3.5                       # examples/FIRFarrow.jl:25-27
+    phase, throwaway = np.modf(delay)
+    f, o = mr.FIRFilter(*args), mo.FIRFilter(*args)
+    f.kernel.inputDeficit += int(throwaway)
+    o.kernel.inputDeficit += int(throwaway)
+    assert f.setphase(phase) == o.setphase(phase)
+    for a, b in ((0, 3), (3, 2600), (2600, 5000)):                   # the first chunk is shorter than the deficit
+        y, w = f.filt(x[:, a:b]), o.filt(x[:, a:b])
+        assert y.shape == w.shape
+        assert nerr(y, w) <= 1e-12
+        assert states_equal(f, o)
+
+
+@pytest.mark.parametrize("polyorder", [None, 4])
+@pytest.mark.parametrize("tx", [np.float32, np.float64])
+def test_segment_split_arbitrary_and_farrow(polyorder, tx, rng):
+    """a long stream through an arbitrary-rate / Farrow resampler split into independent segments.
+    Each segment's filter is seeked by exact replay and given the preceding samples as halo; counts, first-output
+    indices and end states are exact, values match the single-stream run (and the oracle on a slice)."""
+    import torch
+    N, rate = 32, 0.918734
+    h = (mo.firdes(12 * N, 0.45 / N, 5.6533) * N).astype(tx)
+    args = (h, rate, N) if polyorder is None else (h, rate, N, polyorder)
+    nch, n = 3, 150_001
+    x = rand_samples(rng, (nch, n), tx)
+    xd = torch.from_numpy(x).cuda()
+    whole_f = mr.FIRFilter(*args)
+    whole = whole_f.filt(xd)
+    plan = mr.segment_plan(whole_f, n, 4, align=1)
+    assert [p[0] for p in plan][0] == 0 and plan[-1][1] == n
+    parts = []
+    for n0, n1, k0, cnt in plan:
+        f = mr.FIRFilter(*args, nchannels=nch, sample_dtype=tx)
+        H = f.historyLen
+        halo = xd[:, n0 - H:n0].contiguous() if n0 > 0 else None
+        assert f.seek(n0, halo) == k0 == sum(p.shape[1] for p in parts)
+        y = f.filt(xd[:, n0:n1])
+        assert y.shape[1] == cnt
+        parts.append(y)
+    got = torch.cat(parts, dim=1)
+    assert got.shape == whole.shape
+    assert (got - whole).abs().max().item() <= tol_for(tx) * whole.abs().max().item()
+    s_seg, s_whole = f._get_state(), whole_f._get_state()
+    assert (s_seg.phi_idx, s_seg.input_deficit, s_seg.phi_accumulator, s_seg.alpha) == \
+           (s_whole.phi_idx, s_whole.input_deficit, s_whole.phi_accumulator, s_whole.alpha)
+    o = mo.FIRFilter(*args)
+    w = o.filt(x[0, :20000])
+    assert nerr(got[0, :len(w)].cpu().numpy(), w) <= tol_for(tx)
+
+
 @pytest.mark.parametrize("L,ntaps,nch", [(1, 128, 33), (1, 97, 5), (1, 31, 64), (2, 200, 40), (2, 66, 1), (4, 512, 31),
                                           (4, 390, 96)])
 @pytest.mark.parametrize("tx", [np.float32, np.complex64])

@@ -152,3 +152,25 @@ def test_seek_closed_form(L, M, rng):
         F.check(F.lib().mrb_seek(a._handle, n0, None, 0, C.byref(k0), None))
         assert advance(b, n0) == k0.value
         assert state_tuple(a)[:2] == state_tuple(b)[:2]
+
+
+@pytest.mark.parametrize("polyorder", [None, 4])
+@pytest.mark.parametrize("rate", [0.918734, 1.37, 1 / 2.123456789, 3.0001])
+def test_seek_table_kinds_is_the_exact_replay(rate, polyorder, rng):
+    """seek(n0) of an arbitrary / Farrow filter == the state after consuming n0 samples, bit for bit
+    (phase accumulator, alpha, deficit), however the n0 samples were chunked; k0 == the outputs produced so far."""
+    h = rng.random(32 * 12)
+    args = (h, rate, 32) if polyorder is None else (h, rate, 32, polyorder)
+    for n0 in [0, 1, 2, 31, 1000, 65536 + 17, 1_000_003]:
+        a = mr.FIRFilter(*args, nchannels=1, sample_dtype=np.float32, device=-1)
+        b = mr.FIRFilter(*args, nchannels=1, sample_dtype=np.float32, device=-1)
+        assert a.seek(n0) == advance(b, n0 // 3) + advance(b, n0 - n0 // 3)
+        assert state_tuple(a) == state_tuple(b)
+        # and against the oracle's literal loop for the sizes it finishes quickly
+        if n0 <= 70000:
+            o = mo.FIRFilter(*args)
+            assert len(o.filt(np.zeros(n0))) == a.seek(n0)
+            so = o.state()
+            assert a._get_state().input_deficit == so["inputDeficit"]
+            if "acc" in so:
+                assert a._get_state().phi_accumulator == so["acc"]
