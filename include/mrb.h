@@ -147,6 +147,13 @@ int32_t mrb_get_pfb(const mrb_filter *f, int32_t which, void *dst);
  * halo + c*ld_halo; NULL = zeros).  *k0 receives the absolute index of the segment's first output. */
 int32_t mrb_seek(mrb_filter *f, int64_t n0, const void *halo, int64_t ld_halo, int64_t *k0, void *stream);
 
+/* Live tap update (no reference counterpart -- upstream rebuilds the FIRFilter; SURVEY 8f rank 3, host side).
+ * Replaces the taps in place: h has the tap dtype and length given at creation, so taps-per-phase, history
+ * length, the carried phase state and the per-channel history are all kept.  Banks are rebuilt as mrb_create
+ * builds them (src/Filters.jl:21,36,53,73,106-108,138-139); Farrow needs the new host-fitted poly_coeffs
+ * (else NULL).  Synchronises the device. */
+int32_t mrb_set_taps(mrb_filter *f, const void *h, int64_t h_len, const double *poly_coeffs);
+
 /* number of CUDA kernels this handle has launched (bench.py's gpu_launches) */
 int32_t mrb_launch_count(const mrb_filter *f, int64_t *n);
 /* Kernel timing for bench.py's roofline: when on, every mrb_filt brackets its FILTER kernel(s) (not the

@@ -250,6 +250,55 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
     return MRB_OK;
 }
 
+// Live tap update (host side): replace the taps of a filter in place -- same length and tap dtype,
+// so T, H, the carried phase state and the per-channel history all stay as they are -- e.g. an adaptive filter whose
+// taps change between chunks.  The banks are rebuilt exactly as mrb_create builds them (flipud / taps2pfb /
+// [diff(h);0] / the caller's Farrow fit) and every kernel's copy is refreshed.  Synchronises the device.
+extern "C" int32_t mrb_set_taps(mrb_filter *f, const void *hv, int64_t h_len, const double *poly_coeffs) {
+    if (!f || !hv) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
+    if (h_len != f->hLen) return fail(MRB_ERR_BAD_ARGUMENT, "mrb_set_taps keeps the tap count (%lld), got %lld", (long long)f->hLen, (long long)h_len);
+    if (f->kind == MRB_FARROW && !poly_coeffs) return fail(MRB_ERR_BAD_ARGUMENT, "farrow needs host-fitted poly_coeffs");
+    std::vector<double> h((size_t)h_len);
+    for (int64_t i = 0; i < h_len; ++i)
+        h[i] = f->th == MRB_F32 ? (double)static_cast<const float *>(hv)[i] : static_cast<const double *>(hv)[i];
+    if (f->kind == MRB_STANDARD || f->kind == MRB_DECIMATOR) {
+        for (size_t i = 0; i < h.size(); ++i) f->bank[i] = h[h.size() - 1 - i];            // flipud(h), :21,:53
+    } else {
+        make_bank(h, f->Nphi, f->T, f->bank);                                              // taps2pfb, :36,:73,:107,:138
+    }
+    if (f->kind == MRB_ARBITRARY) {
+        std::vector<double> dh(h.size(), 0.0);                                             // :106
+        for (size_t i = 0; i + 1 < h.size(); ++i)
+            dh[i] = f->th == MRB_F32 ? (double)((float)h[i + 1] - (float)h[i]) : h[i + 1] - h[i];
+        make_bank(dh, f->Nphi, f->T, f->dbank);
+    }
+    if (f->kind == MRB_FARROW) f->pnfb.assign(poly_coeffs, poly_coeffs + f->T * (f->polyorder + 1));
+    if (f->device < 0) return MRB_OK;
+
+    CU(cudaSetDevice(f->device));
+    CU(cudaDeviceSynchronize());                       // kernels in flight still read the old banks
+    const bool dbl = is_double(f->ty);
+    auto refresh = [&](const std::vector<double> &src, void *dst) -> cudaError_t {
+        if (dbl) return cudaMemcpy(dst, src.data(), src.size() * sizeof(double), cudaMemcpyHostToDevice);
+        std::vector<float> tmp(src.begin(), src.end());
+        return cudaMemcpy(dst, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice);
+    };
+    CU(refresh(f->bank, f->d_bank));
+    if (f->kind == MRB_ARBITRARY) CU(refresh(f->dbank, f->d_dbank));
+    if (f->kind == MRB_FARROW) CU(cudaMemcpy(f->d_pnfb, f->pnfb.data(), f->pnfb.size() * sizeof(double), cudaMemcpyHostToDevice));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, f->device));
+    tiled_release(f->tiled); unit_release(f->unit); decim_release(f->decim);
+    int32_t rc = tiled_prepare(f->tiled, f->kind, f->tx, f->ty, f->L, f->M, f->Nphi, f->T, f->bank, f->dbank, prop);
+    if (rc != 0) return fail(MRB_ERR_CUDA, "tiled_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
+    rc = unit_prepare(f->unit, f->kind, f->tx, f->ty, f->L, f->M, f->T, f->bank, prop);
+    if (rc != 0) return fail(MRB_ERR_CUDA, "unit_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
+    rc = decim_prepare(f->decim, f->kind, f->tx, f->ty, f->L, f->M, f->T, f->bank, prop);
+    if (rc != 0) return fail(MRB_ERR_CUDA, "decim_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
+    CU(cudaDeviceSynchronize());
+    return MRB_OK;
+}
+
 extern "C" int32_t mrb_destroy(mrb_filter *f) {
     if (!f) return MRB_OK;
     free_device(f);

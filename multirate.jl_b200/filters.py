@@ -469,6 +469,20 @@ class FIRFilter:
         self._pending_state = None
         return self
 
+    def set_taps(self, h):
+        """Replace the taps in place (same length and dtype), keeping phase state and history -- an adaptive filter whose
+        taps change between chunks (upstream would rebuild the FIRFilter and lose its state)."""
+        h = np.ascontiguousarray(h, dtype=self._h.dtype)
+        if h.shape != self._h.shape:
+            raise ValueError("set_taps keeps the tap count (%d)" % len(self._h))
+        self._h = h
+        if self._kind == _ffi.FARROW:
+            self._pnfb = np.ascontiguousarray(pfb2pnfb(taps2pfb(h, self._n_phi), self._polyorder))
+        if self._handle is not None:
+            _ffi.check(_ffi.lib().mrb_set_taps(self._handle, h.ctypes.data, len(h),
+                                               self._pnfb.ctypes.data if self._pnfb is not None else None))
+        return self
+
     def seek(self, n0, halo=None):
         """Long-stream segment start (no reference counterpart): put the filter in the state it
         would have after consuming `n0` samples since construction, with `halo` = the historyLen samples preceding n0

@@ -283,6 +283,49 @@ def test_segment_split_matches_stream(rng):
     assert (got - whole).abs().max().item() <= 1e-6 * whole.abs().max().item()
 
 
+@pytest.mark.parametrize("case", ["rational_tiled", "standard_unit", "decimator", "arbitrary", "farrow", "rational_f64"])
+def test_live_tap_update(case, rng):
+    """SURVEY 8f rank 3 (host side): taps replaced between chunks with state and history carried -- every fast kernel's
+    private copy of the bank must follow.  Oracle twin: a fresh oracle filter with the new taps that inherits the old
+    one's kernel state and history."""
+    import torch
+    tx, nch, n, cut = np.complex64, 130, 24000, 12000                # cut keeps the second chunk 16-byte aligned
+    if case == "rational_tiled":
+        mk = lambda: (rng.standard_normal(24 * 7).astype(np.float32), Fraction(7, 8))
+    elif case == "standard_unit":
+        tx = np.float32
+        mk = lambda: (rng.standard_normal(100).astype(np.float32), Fraction(1, 1))
+    elif case == "decimator":
+        mk = lambda: (rng.standard_normal(200).astype(np.float32), Fraction(1, 8))
+    elif case == "arbitrary":
+        tx = np.float32
+        mk = lambda: (rng.standard_normal(32 * 9).astype(np.float32), 0.918734, 32)
+    elif case == "farrow":
+        tx = np.float32
+        mk = lambda: (rng.standard_normal(32 * 9).astype(np.float32), 0.918734, 32, 3)
+    else:
+        tx, nch = np.float64, 2
+        mk = lambda: (rng.standard_normal(24 * 7), Fraction(7, 8))
+    a1, a2 = mk(), mk()
+    x = rand_samples(rng, (nch, n), tx)
+    xd = torch.from_numpy(x).cuda()
+    f, o = mr.FIRFilter(*a1), mo.FIRFilter(*a1)
+    y1, w1 = f.filt(xd[:, :cut]), o.filt(x[:3, :cut])
+    assert nerr(y1[:3].cpu().numpy(), w1) <= tol_for(y1.cpu().numpy().dtype)
+    first_kernel = f.last_kernel
+    f.set_taps(a2[0])
+    o2 = mo.FIRFilter(*a2)
+    o2.history = o.history
+    for name in ("phiIdx", "inputDeficit", "phiAccumulator", "alpha", "xIdx"):
+        if hasattr(o.kernel, name):
+            setattr(o2.kernel, name, getattr(o.kernel, name))
+    y2, w2 = f.filt(xd[:, cut:]), o2.filt(x[:3, cut:])
+    assert y2.shape[1] == w2.shape[1]
+    assert nerr(y2[:3].cpu().numpy(), w2) <= tol_for(y2.cpu().numpy().dtype)
+    assert states_equal(f, o2)
+    assert f.last_kernel == first_kernel and first_kernel != "generic"
+
+
 @pytest.mark.parametrize("case", ["farrow", "arbitrary", "rational"])
 def test_output_time_offset_api(case, rng):
     """the documented use of setphase (examples/FIRFarrow.jl:25-30) -- throw away whole samples by

@@ -174,3 +174,23 @@ def test_seek_table_kinds_is_the_exact_replay(rate, polyorder, rng):
             assert a._get_state().input_deficit == so["inputDeficit"]
             if "acc" in so:
                 assert a._get_state().phi_accumulator == so["acc"]
+
+
+def test_set_taps_rebuilds_banks_and_keeps_state(rng):
+    """SURVEY 8f rank 3 (host side): mrb_set_taps rebuilds pfb / dpfb / flipped h exactly as construction does and
+    leaves the carried state alone; wrong length is refused."""
+    for args in ((Fraction(3, 17),), (Fraction(1, 4),), (0.77, 8), (0.77, 8, 3)):
+        h1, h2 = rng.random(50), rng.random(50)
+        f = mr.FIRFilter(h1, *args, nchannels=1, sample_dtype=np.float64, device=-1)
+        advance(f, 1234)
+        before = state_tuple(f)
+        f.set_taps(h2)
+        g = mr.FIRFilter(h2, *args, nchannels=1, sample_dtype=np.float64, device=-1)
+        assert np.array_equal(f._pfb(0), g._pfb(0))
+        if len(args) == 2:
+            assert np.array_equal(f._pfb(1), g._pfb(1))
+        assert state_tuple(f) == before
+        with pytest.raises(ValueError):
+            f.set_taps(h2[:-1])
+        with pytest.raises(mr.MrbError):
+            F.check(F.lib().mrb_set_taps(f._handle, h2.ctypes.data, 49, None))
