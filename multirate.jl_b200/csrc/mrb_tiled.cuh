@@ -44,7 +44,11 @@
 namespace mrb {
 
 constexpr int kTiledRows = 128;         // channels per CTA
-constexpr int kBoxSamples = 8;          // samples per TMA box row (64 B for complex64)
+#ifndef MRB_BOX_SHIFT
+#define MRB_BOX_SHIFT 4
+#endif
+constexpr int kBoxShift = MRB_BOX_SHIFT;                    // 3: 64-byte box rows (SWIZZLE_64B), 4: 128-byte (SWIZZLE_128B)
+constexpr int kBoxSamples = 1 << kBoxShift;                 // samples per TMA box row
 constexpr int kBoxBytes = kTiledRows * kBoxSamples * 8;     // 8192
 constexpr int kOutChunk = 8;            // outputs per staged TMA store (64-byte rows)
 constexpr int kOutBufs = 4;
@@ -52,9 +56,9 @@ constexpr int kOutBytes = kTiledRows * kOutChunk * 8;       // 8192
 constexpr int kBankFloats = 6000;       // tap bank capacity in kernel-parameter space
 constexpr int kMaxTiles = 192;          // time tiles per launch (their start states ride in parameter space)
 constexpr int kMaxPhases = 1024;
-constexpr int kTPAD = 24, kRMAX = 12, kNBOX = 10;
+constexpr int kTPAD = 24, kRMAX = 12, kNBOX = 80 / kBoxSamples;   // the ring holds 80 samples per channel
 constexpr int kOB = 2;                  // outputs per basic block of the run body (1, 2 and 3 measure the same)
-constexpr int kRingPairs = 4 * kNBOX;   // sample pairs (16-byte chunks per row) the ring holds
+constexpr int kRingPairs = kBoxSamples / 2 * kNBOX;   // sample pairs (16-byte chunks per row) the ring holds
 constexpr int kWinLen = (kRingPairs + (kTPAD + kRMAX) / 2 + 8 + 3) / 4 * 4;
 
 struct alignas(16) TiledParams {
@@ -204,7 +208,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     constexpr int RW = RMAX / 2;                          // outputs per warp per run
     constexpr int NP = (TPAD + RW + 1) / 2;               // sample pairs one warp's outputs touch
     constexpr int NPRUN = (TPAD + RMAX + 1) / 2;          // sample pairs the whole run touches
-    static_assert(2 * NPRUN + 7 <= (NBOX - 1) * kBoxSamples, "the ring must hold a run's window and leave a box to refill");
+    static_assert(2 * NPRUN + kBoxSamples - 1 <= (NBOX - 1) * kBoxSamples, "the ring must hold a run's window and leave a box to refill");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *in_ring = smem;                                   // NBOX boxes [128][8] complex64, SWIZZLE_64B
     unsigned char *out_ring = smem + NBOX * kBoxBytes;               // kOutBufs chunks [128][8] complex64, SWIZZLE_64B
@@ -215,8 +219,10 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     const int half = __shfl_sync(0xffffffffu, tid >> 7, 0);          // warp-uniform by construction (keeps taps on LDCU)
     const int ch0 = blockIdx.y * kTiledRows;
     const uint32_t in_base = smem_u32(in_ring), out_base = smem_u32(out_ring), bar_base = smem_u32(bars);
-    // SWIZZLE_64B: the 16-byte chunk index is XORed with (row >> 1) & 3.  The per-lane part of every address:
+    // SWIZZLE_64B: the 16-byte chunk index is XORed with (row >> 1) & 3; SWIZZLE_128B: with row & 7.  The per-lane
+    // part of every address, for the output staging buffers (64-byte rows) and for the input ring:
     const uint32_t rowpart = ((uint32_t)row * 64u) ^ ((((uint32_t)row >> 1) & 3u) << 4);
+    const uint32_t rowpart_in = kBoxShift == 3 ? rowpart : ((uint32_t)row * 128u) ^ (((uint32_t)row & 7u) << 4);
 
     // ---- tile start state: from parameter space (uniform)
     const int ka_rel = blockIdx.x * P.KT;                              // relative to k_begin
@@ -226,7 +232,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     const int xc0 = P.tile[blockIdx.x].xc0;                            // float coordinate of box 0 in tmx
     const int yc0 = ((int)P.k_begin + ka_rel) * 2;
     // boxes this tile is expected to touch (prefetch bound); demand may exceed it by a box or two
-    const int jend = ((ntile + (int)(((long long)ntile * (P.M - P.L)) / P.L) + TPAD + RMAX) >> 3) + 1;
+    const int jend = ((ntile + (int)(((long long)ntile * (P.M - P.L)) / P.L) + TPAD + RMAX) >> kBoxShift) + 1;
 
     if (tid == 0) {
         if (in_base & 1023u) __trap();                               // the swizzle formulas assume 1 KiB alignment
@@ -238,7 +244,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 #pragma unroll 1
         for (int jj = 0; jj < NBOX; ++jj) {                          // prologue: fill the ring
             mbar_expect_tx(bar_base + 8 * jj, kBoxBytes);
-            tma_load_2d(in_base + (uint32_t)(jj * kBoxBytes), &tmx, xc0 + jj * 16, ch0, bar_base + 8 * jj);
+            tma_load_2d(in_base + (uint32_t)(jj * kBoxBytes), &tmx, xc0 + jj * (2 * kBoxSamples), ch0, bar_base + 8 * jj);
         }
     }
     __syncthreads();
@@ -253,9 +259,9 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         const int rt = P.runtab[j];
         const int len = min(rt & 0xff, ntile - k);
         const int A = s & ~1;                                  // aligned window start
-        const int jneed = (A + 2 * NPRUN - 1) >> 3;            // newest box the run's windows touch
+        const int jneed = (A + 2 * NPRUN - 1) >> kBoxShift;    // newest box the run's windows touch
         const int q_done = k >> 3;                             // chunks completed by earlier runs
-        const int p = ((A >> 1) + half * (RW / 2)) % (4 * NBOX);   // ring position (in pairs) of this warp's window
+        const int p = ((A >> 1) + half * (RW / 2)) % kRingPairs;   // ring position (in pairs) of this warp's window
         const unsigned *wt = P.win[p & 3] + (p & ~3);
 
         // ---- this warp's window -> registers
@@ -265,7 +271,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
             if (++w_slot == NBOX) { w_slot = 0; w_par ^= 1u; }
         }
         unsigned long long xw[2 * NP];
-        load_window<NP>(xw, wt, in_base, rowpart);
+        load_window<NP>(xw, wt, in_base, rowpart_in);
 
         // ---- the one barrier of the run.  Behind it (a) every warp holds its window in registers, so all boxes
         // before the NEXT run's window are free and are refilled now, a whole run ahead of their first use; (b) every
@@ -273,9 +279,9 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         // the run ended on a phase wrap: the input index then skips one sample (M > L) or repeats one (M < L)
         const int s_next = s + len + ((rt >> 8) & 1) - ((rt >> 9) & 1);
         const bool has_next = k + len < ntile;
-        const int jA_next = (has_next ? s_next : s) >> 3;
+        const int jA_next = (has_next ? s_next : s) >> kBoxShift;
         // the next run's windows must be on their way after this barrier whatever the estimate `jend` says
-        const int jneed_next = has_next ? ((s_next & ~1) + 2 * NPRUN - 1) >> 3 : jneed;
+        const int jneed_next = has_next ? ((s_next & ~1) + 2 * NPRUN - 1) >> kBoxShift : jneed;
         const bool flush = q_done > q_flushed;
         if (flush) fence_async_smem();                         // this thread's st.shared -> visible to the async proxy
         if (tid == 0) tma_wait_read<0>();                      // stores issued a run ago have left their buffers
@@ -287,7 +293,7 @@ k_tiled_c64(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
             for (int jj = j_issued; jj <= jtarget; ++jj) {
                 const uint32_t bar = bar_base + 8 * sl;
                 mbar_expect_tx(bar, kBoxBytes);
-                tma_load_2d(in_base + (uint32_t)(sl * kBoxBytes), &tmx, xc0 + jj * 16, ch0, bar);
+                tma_load_2d(in_base + (uint32_t)(sl * kBoxBytes), &tmx, xc0 + jj * (2 * kBoxSamples), ch0, bar);
                 if (++sl == NBOX) sl = 0;
             }
             // The run writes chunks q_done.. ; the stores issued here read the buffers of chunks q_flushed..q_done-1
@@ -397,7 +403,7 @@ static inline int32_t tiled_prepare(TiledPlan &p, int kind, int tx, int ty, int6
     for (int c = 0; c < 4; ++c)
         for (int i = 0; i < kWinLen; ++i) {
             const unsigned u = (unsigned)(c + i) % (unsigned)kRingPairs;
-            p.hp->win[c][i] = ((u & 3u) << 4) | ((u >> 2) * (unsigned)kBoxBytes);
+            p.hp->win[c][i] = ((u & (unsigned)(kBoxSamples / 2 - 1)) << 4) | ((u >> (kBoxShift - 1)) * (unsigned)kBoxBytes);
         }
     for (int i = 0; i < 48; ++i) {
         const unsigned kk = (unsigned)i & 31u;
@@ -470,10 +476,10 @@ static inline int64_t tiled_try_launch(TiledPlan &p, const GenParams &G, cudaStr
         const int64_t ka = k_begin + i * P.KT;
         const int64_t t0 = G.p0 + ka * G.M;
         const int64_t xs0 = G.d0m1 + t0 / G.L - (p.tpad - 1);         // x-sample index of the first window start
-        const int64_t box0 = xs0 >> 3;
+        const int64_t box0 = xs0 >> kBoxShift;
         P.tile[i].j = p.row_of_phase[(size_t)(t0 % G.L)];
-        P.tile[i].s = (int)(xs0 - (box0 << 3));
-        P.tile[i].xc0 = (int)(box0 << 3) * 2;
+        P.tile[i].s = (int)(xs0 - (box0 << kBoxShift));
+        P.tile[i].xc0 = (int)(box0 << kBoxShift) * 2;
     }
     CUtensorMap tmx, tmy;
     {
@@ -484,8 +490,8 @@ static inline int64_t tiled_try_launch(TiledPlan &p, const GenParams &G, cudaStr
         // 256-byte L2 promotion: DRAM sees 256-byte bursts per channel row although a box row is 64 bytes
         // (tools/ubench3.cu: +10 % read bandwidth for this access pattern)
         if (p.encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(G.x), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, kBoxShift == 3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return -1;
         cuuint64_t ydims[2] = {(cuuint64_t)(2 * G.nout), (cuuint64_t)G.nch};
         cuuint64_t ystrides[1] = {(cuuint64_t)G.ldy * 8};
