@@ -158,6 +158,19 @@ function setphase(f::FIRFilter, ϕ::Real)
     check(ccall((:mrb_setphase, libmrb), Int32, (Ptr{Cvoid}, Float64), hosthandle(f), ϕ))
     s = MrbState(); check(ccall((:mrb_get_state, libmrb), Int32, (Ptr{Cvoid}, Ref{MrbState}), f.handle, s)); s
 end
+# long-stream segment start (no upstream counterpart): state after n0 consumed samples; halo = the historyLen samples
+# before n0 as a device pointer (C_NULL = zeros), one row of ldhalo samples per channel.  Returns the first output index.
+function seek!(f::FIRFilter, n0::Integer, halo::Ptr{Cvoid}=C_NULL, ldhalo::Integer=0, stream::Ptr{Cvoid}=C_NULL)
+    k0 = Ref{Int64}(0)
+    check(ccall((:mrb_seek, libmrb), Int32, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ref{Int64}, Ptr{Cvoid}),
+                hosthandle(f), n0, halo, ldhalo, k0, stream)); k0[]
+end
+# live tap update (no upstream counterpart): same tap count, phase state and history kept; Farrow filters pass the
+# refitted coefficients (pfb2pnfb of the new taps, T x (order+1), row-major)
+function settaps!(f::FIRFilter{Tk,Th}, h::Vector{Th}, polycoeffs::Union{Nothing,Vector{Float64}}=nothing) where {Tk,Th}
+    check(ccall((:mrb_set_taps, libmrb), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}),
+                hosthandle(f), h, length(h), polycoeffs === nothing ? C_NULL : pointer(polycoeffs))); f
+end
 function outputlength(f::FIRFilter, inputlength::Integer)                  # src/Filters.jl:352-385
     r = Ref{Int64}(0)
     check(ccall((:mrb_outputlength, libmrb), Int32, (Ptr{Cvoid}, Int64, Ref{Int64}), hosthandle(f), inputlength, r)); r[]
