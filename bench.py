@@ -6,7 +6,7 @@ through a stateful FIRFilter (history, phase and deficit carried on the device b
 
 Default workload (N=1 and every N, weak scaling): BASELINE.json configs[4]'s per-GPU shard --
 FIRRational 147//160, 3528-tap Kaiser low-pass (Float32 taps), 8192 channels of Complex64 per GPU
-(65,536 channels over 8 GPUs), 64K-sample chunks.  Other configs: --workload c1|c2|c3a|c3b|c4a|c4f|c4a64|c4f64.
+(65,536 channels over 8 GPUs), 64K-sample chunks.  Other configs: --workload c1|c2|c3a|c3b|c4a|c4f|c4a64|c4f64 (and x* extras).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5] [--impl reference]
 """
@@ -48,6 +48,19 @@ WORKLOADS = {
               0.918734, 2336, 0.45 / 32, 5.6533, 32.0, np.float64, 1024, 32, None),
     "c4f64": ("FIRFarrow rate 0.918734, Nphi 32, 2336 taps, order 4, 1024 ch float64 (BASELINE configs[3])",
               0.918734, 2336, 0.45 / 32, 5.6533, 32.0, np.float64, 1024, 32, 4),
+    # extras (not BASELINE configs): the same kernels on the other sample type / the mirrored ratio
+    "x160": ("extra: FIRRational 160//147, 3840 taps, 8192 ch complex64", Fraction(160, 147), 3840, 0.5 / 160, 7.8562, 1.0,
+             np.complex64, 8192, None, None),
+    "x2f": ("extra: FIRDecimator 1//8, 256 taps, 4096 ch float32", Fraction(1, 8), 256, 0.5 / 8, 7.8562, 1.0,
+            np.float32, 4096, None, None),
+    "x3ac": ("extra: FIRInterpolator 4//1, 128 taps, 4096 ch complex64", Fraction(4, 1), 128, 0.5 / 4, 7.8562, 4.0,
+             np.complex64, 4096, None, None),
+    "x3bc": ("extra: FIRStandard, 128 taps, 4096 ch complex64", Fraction(1, 1), 128, 0.25, 7.8562, 1.0,
+             np.complex64, 4096, None, None),
+    "x4ac": ("extra: FIRArbitrary rate 0.918734, Nphi 32, 2336 taps, 1024 ch complex64", 0.918734, 2336, 0.45 / 32,
+             5.6533, 32.0, np.complex64, 1024, 32, None),
+    "x4fc": ("extra: FIRFarrow rate 0.918734, Nphi 32, 2336 taps, order 4, 1024 ch complex64", 0.918734, 2336, 0.45 / 32,
+             5.6533, 32.0, np.complex64, 1024, 32, 4),
 }
 
 
@@ -336,7 +349,8 @@ def main():
                 "peak_source": peak_src}
     # FP32 side of the roofline: real FMAs the kernel executes per output and channel.  Only the 147//160
     # shard (c5) is HBM-bound; decimator-256, standard-128 and the arbitrary-rate kernels sit on the FP32 roof.
-    taps_per_out = {"c5": 24, "c1": 24, "c2": 256, "c3a": 32, "c3b": 128, "c4a": 73, "c4f": 73, "c4a64": 73, "c4f64": 73}[w]
+    taps_per_out = {"c5": 24, "c1": 24, "c2": 256, "c3a": 32, "c3b": 128, "c4a": 73, "c4f": 73, "c4a64": 73, "c4f64": 73,
+                    "x160": 24, "x2f": 256, "x3ac": 32, "x3bc": 128, "x4ac": 73, "x4fc": 73}[w]
     flops = 2 * taps_per_out * (2 if np.dtype(tx).kind == "c" else 1)
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                       # nominal, TFLOP/s
     if kms:
@@ -347,7 +361,7 @@ def main():
                                     if w == "c4a" else None}
         if w.startswith("c4") and w.endswith("64"):
             roofline["fp32"]["note"] = "Float64 FMAs; the nominal FP64 peak is half the FP32 figure"
-        if w in ("c2", "c3b", "c4a", "c4f", "c4a64", "c4f64"):
+        if w in ("c2", "c3b", "c4a", "c4f", "c4a64", "c4f64", "x2f", "x3bc", "x4ac", "x4fc"):
             roofline["bound"] = "fp32 (see roofline.fp32; hbm fields kept for reference)"
     tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % w)
     if os.path.exists(tr):
