@@ -215,14 +215,22 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                     for (int o = 0; o < OPW; ++o) {
                         const R *tr = rowg + o * P.rowlen + bb * TB;
                         if constexpr (K == TAB_F32) {
+                            // the two partial sums of an output are one packed pair: (even taps, odd taps) x (even
+                            // samples, odd samples) is one FFMA2 on two aligned register pairs -- half the issue slots
+                            unsigned long long a2;
+                            asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "f"(acc[o][0]), "f"(acc[o][1]));
 #pragma unroll
                             for (int q = 0; q < TB / 4; ++q) {
                                 const float4 t = reinterpret_cast<const float4 *>(tr)[q];
-                                acc[o][0] = fmaf(t.x, w[4 * q], acc[o][0]);
-                                acc[o][1] = fmaf(t.y, w[4 * q + 1], acc[o][1]);
-                                acc[o][0] = fmaf(t.z, w[4 * q + 2], acc[o][0]);
-                                acc[o][1] = fmaf(t.w, w[4 * q + 3], acc[o][1]);
+                                unsigned long long t01, t23, w01, w23;
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(t01) : "f"(t.x), "f"(t.y));
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(t23) : "f"(t.z), "f"(t.w));
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(w01) : "f"(w[4 * q]), "f"(w[4 * q + 1]));
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(w23) : "f"(w[4 * q + 2]), "f"(w[4 * q + 3]));
+                                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a2) : "l"(t01), "l"(w01));
+                                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a2) : "l"(t23), "l"(w23));
                             }
+                            asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[o][0]), "=f"(acc[o][1]) : "l"(a2));
                         } else if constexpr (K == TAB_F64) {
 #pragma unroll
                             for (int q = 0; q < TB / 2; ++q) {
@@ -231,14 +239,21 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                                 acc[o][1] = fma(t.y, w[2 * q + 1], acc[o][1]);
                             }
                         } else {                                     // complex sample i = (w[2i], w[2i+1]), real tap
+                            // one FFMA2 per tap: (re, im) += t * (re, im), the tap a scalar register operand
+                            unsigned long long a2;
+                            asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "f"(acc[o][0]), "f"(acc[o][1]));
 #pragma unroll
                             for (int q = 0; q < TB / 4; ++q) {
                                 const float4 t = reinterpret_cast<const float4 *>(tr)[q];
-                                acc[o][0] = fmaf(t.x, w[8 * q], acc[o][0]);     acc[o][1] = fmaf(t.x, w[8 * q + 1], acc[o][1]);
-                                acc[o][0] = fmaf(t.y, w[8 * q + 2], acc[o][0]); acc[o][1] = fmaf(t.y, w[8 * q + 3], acc[o][1]);
-                                acc[o][0] = fmaf(t.z, w[8 * q + 4], acc[o][0]); acc[o][1] = fmaf(t.z, w[8 * q + 5], acc[o][1]);
-                                acc[o][0] = fmaf(t.w, w[8 * q + 6], acc[o][0]); acc[o][1] = fmaf(t.w, w[8 * q + 7], acc[o][1]);
+                                const float tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    unsigned long long xs;
+                                    asm("mov.b64 %0, {%1, %2};" : "=l"(xs) : "f"(w[8 * q + 2 * e]), "f"(w[8 * q + 2 * e + 1]));
+                                    cfma(a2, tt[e], xs);
+                                }
                             }
+                            asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[o][0]), "=f"(acc[o][1]) : "l"(a2));
                         }
                     }
                 }
