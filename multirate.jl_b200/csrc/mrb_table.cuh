@@ -109,14 +109,17 @@ struct alignas(16) TabParams {
     unsigned win[4][160];      // win[c][i] = W((c + i) mod 8 NB): chunk bits | ring slot offset of 16-byte chunk u
 };
 
-template <int K>
+// TB = row elements (window samples) per tap block: TabCfg<K>::TB, or the next smaller size when the rows fit it
+// (every element of a row is a tap load and an FMA for all channels, zero padding included)
+template <int K, int TB>
 __global__ void __launch_bounds__(128, 3)
 k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
             const typename TabCfg<K>::Tap *__restrict__ rows, const int32_t *__restrict__ astart,
             const __grid_constant__ TabParams P) {
     using C = TabCfg<K>;
     using R = typename C::Tap;
-    constexpr int A = C::A, TB = C::TB, NQ = TB / A, NB = C::NB, ES = C::ES;
+    constexpr int A = C::A, NQ = TB / A, NB = C::NB, ES = C::ES;
+    static_assert(TB % 4 == 0 && TB <= C::TB, "tap rows are read four (two) at a time");
     constexpr int BOX_BYTES = kTabRows * 128;
     constexpr int OPW = kTabStep / kTabWarps;                        // outputs per warp per step
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -200,6 +203,7 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                         const unsigned ww[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
+                            if (q + e >= NQ) break;
                             const uint32_t ad = in_base + (rowpart ^ ww[e]);
                             if constexpr (K == TAB_F64) {
                                 asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
@@ -357,6 +361,10 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
     const int64_t gspan = rate > 0.0 ? (int64_t)std::ceil((kTabGroup - 1) / rate) + 1 : (int64_t)1 << 20;
     p.nblk = (int)ceil_div(T + p.A - 1 + gspan, p.TB);
     if (p.nblk > 2) return 0;                                            // taps too long / rate too low for a shared window
+    {   // the next smaller block (22 instead of 24 16-byte chunks) when the rows still fit the same number of blocks
+        const int tbr = p.TB / 12 * 11;
+        if (ceil_div(T + p.A - 1 + gspan, (int64_t)tbr) == p.nblk) p.TB = tbr;
+    }
     p.rowlen = p.nblk * p.TB;
     p.hp = new TabParams();
     memset(p.hp, 0, sizeof(TabParams));
@@ -367,9 +375,13 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
             p.hp->win[c][i] = ((u & 7u) << 4) | ((u >> 3) * (unsigned)(kTabRows * 128));
         }
     const int smem = table_smem(p);
-    e = p.K == TAB_F32 ? cudaFuncSetAttribute(k_table_fir<TAB_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-      : p.K == TAB_F64 ? cudaFuncSetAttribute(k_table_fir<TAB_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                       : cudaFuncSetAttribute(k_table_fir<TAB_C64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const bool red = p.TB != (p.K == TAB_F32 ? TabCfg<TAB_F32>::TB : TabCfg<TAB_F64>::TB);
+    e = p.K == TAB_F32 ? (red ? cudaFuncSetAttribute(k_table_fir<TAB_F32, 88>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                              : cudaFuncSetAttribute(k_table_fir<TAB_F32, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
+      : p.K == TAB_F64 ? (red ? cudaFuncSetAttribute(k_table_fir<TAB_F64, 44>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                              : cudaFuncSetAttribute(k_table_fir<TAB_F64, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
+                       : (red ? cudaFuncSetAttribute(k_table_fir<TAB_C64, 44>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                              : cudaFuncSetAttribute(k_table_fir<TAB_C64, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (e != cudaSuccess) return (int32_t)e;
     p.ok = true;
     return 0;
@@ -449,9 +461,17 @@ static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind,
 #undef MRB_TAB_SKIP
     dim3 grid((unsigned)groups, (unsigned)tiles);
     const int smem = table_smem(p);
-    if (p.K == TAB_F32) k_table_fir<TAB_F32><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
-    else if (p.K == TAB_F64) k_table_fir<TAB_F64><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)p.d_rows, p.d_astart, P);
-    else k_table_fir<TAB_C64><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+    const bool red = p.TB != (p.K == TAB_F32 ? TabCfg<TAB_F32>::TB : TabCfg<TAB_F64>::TB);
+    if (p.K == TAB_F32) {
+        if (red) k_table_fir<TAB_F32, 88><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+        else k_table_fir<TAB_F32, 96><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+    } else if (p.K == TAB_F64) {
+        if (red) k_table_fir<TAB_F64, 44><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)p.d_rows, p.d_astart, P);
+        else k_table_fir<TAB_F64, 48><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)p.d_rows, p.d_astart, P);
+    } else {
+        if (red) k_table_fir<TAB_C64, 44><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+        else k_table_fir<TAB_C64, 48><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+    }
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
     *name = p.K == TAB_F32 ? "table_f32" : p.K == TAB_F64 ? "table_f64" : "table_c64";
     ++*launches;
