@@ -542,8 +542,12 @@ extern "C" int32_t mrb_get_pfb(const mrb_filter *f, int32_t which, void *dst) {
 // filt
 // ------------------------------------------------------------------------------------------
 template <typename RX, typename R, int NC>
-static void launch_generic(const GenParams &P, cudaStream_t st) {
-    dim3 grid((unsigned)ceil_div(P.nout, 256), (unsigned)std::min<int64_t>(P.nch, 32768));
+static void launch_generic(const GenParams &P0, cudaStream_t st) {
+    GenParams P = P0;
+    P.cpb_log2 = 0;
+    while (P.cpb_log2 < 5 && (128 >> P.cpb_log2) >= P.nout && (2ll << P.cpb_log2) <= P.nch) ++P.cpb_log2;   // short launch: share the block among channels
+    const int64_t W = 256 >> P.cpb_log2, cpb = 1ll << P.cpb_log2;
+    dim3 grid((unsigned)ceil_div(P.nout, W), (unsigned)std::min<int64_t>(ceil_div(P.nch, cpb), 32768));
     k_generic<RX, R, NC><<<grid, 256, 0, st>>>(P);
 }
 
@@ -572,12 +576,32 @@ static bool launch_stream(const GenParams &P, int num_sms, int device, cudaStrea
     return true;
 }
 
+// k_head_warp: short launches (chunk heads) of integer schedules with long windows
+template <typename RX, typename R, int NC>
+static bool launch_head(const GenParams &P, cudaStream_t st) {
+    if (P.mode != SEQ_INTEGER || P.nout > 256 || P.T < 64 || P.nout * P.nch >= (1ll << 26)) return false;
+    // 32x the warps of k_generic: pays when a thread-per-output warp would read M-strided windows (decimating ratios)
+    // or when there are too few outputs to fill the machine with threads (measured: standard-128 x 4096 channels loses)
+    if (P.M < 4 * P.L && P.nout * P.nch >= 8192) return false;
+    k_head_warp<RX, R, NC><<<(unsigned)ceil_div(P.nout * P.nch * 32, 256), 256, 0, st>>>(P);
+    return true;
+}
+
 // Returns the name of the kernel that was launched.  policy != 0 (MRB_POLICY_GENERIC) keeps to k_generic.
 static const char *dispatch_generic(const mrb_filter *f, const GenParams &P, cudaStream_t st) {
     const int key = f->tx * 4 + f->ty;
     const int sms = f->num_sms;
     if (f->policy == 0) {
         bool done = false;
+        switch (key) {
+        case MRB_F32 * 4 + MRB_F32: done = launch_head<float, float, 1>(P, st); break;
+        case MRB_C64 * 4 + MRB_C64: done = launch_head<float, float, 2>(P, st); break;
+        case MRB_F32 * 4 + MRB_F64: done = launch_head<float, double, 1>(P, st); break;
+        case MRB_C64 * 4 + MRB_C128: done = launch_head<float, double, 2>(P, st); break;
+        case MRB_F64 * 4 + MRB_F64: done = launch_head<double, double, 1>(P, st); break;
+        case MRB_C128 * 4 + MRB_C128: done = launch_head<double, double, 2>(P, st); break;
+        }
+        if (done) return "head";
         switch (key) {
         case MRB_F32 * 4 + MRB_F32: done = launch_stream<float, float, 1>(P, sms, f->device, st); break;
         case MRB_C64 * 4 + MRB_C64: done = launch_stream<float, float, 2>(P, sms, f->device, st); break;

@@ -1,6 +1,7 @@
 // mrb_kernels.cuh -- generic (any kind, any dtype, any alignment) sm_100a kernels:
 //   k_generic      one thread per output sample, loops over its channel slice
 //   k_stream       the same for integer schedules, polyphase bank staged in shared memory
+//   k_head_warp    chunk heads of long filters: one warp per output and channel
 //   k_farrow_taps  per-output Farrow tap rows (Float64 Horner, rounded to the tap type)
 //   k_history      history carry  hist <- last H of [hist | x]   (shiftin!, src/support.jl:61-80)
 // The tiled fast paths live in mrb_tiled.cuh; this file is the always-correct path that
@@ -61,14 +62,19 @@ struct GenParams {
     int64_t k_base;             // first output of this launch (index into y and, for SEQ_INTEGER, into the schedule)
     int64_t nout;               // outputs in this launch
     int64_t nch;
+    int32_t cpb_log2;           // k_generic: a block is (256 >> cpb_log2) outputs x (1 << cpb_log2) channels
 };
 
 // y[c, k] = sum_i taps_k[i] * ext[c, n_k + i],  ext = [hist | x]  (H = T-1, so the window of the output
 // whose last sample is x[n_k] starts at ext index n_k).  Reference: src/support.jl:5-55 called from
 // src/Filters.jl:462-468, 505-512, 558-569, 613-625, 717-732, 814-826.
+// Block shape: 256 outputs of one channel, or -- for the short launches that compute a chunk's head (the few outputs whose
+// window reaches the history) -- 256 >> s outputs of 1 << s channels, so that the block's threads all have work.
 template <typename RX, typename R, int NC>
 __global__ void __launch_bounds__(256) k_generic(const GenParams P) {
-    const int64_t kl = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int W = 256 >> P.cpb_log2;
+    const int64_t kl = (int64_t)blockIdx.x * W + (threadIdx.x & (W - 1));
+    const int cl = threadIdx.x >> (8 - P.cpb_log2), cpb = 1 << P.cpb_log2;
     if (kl >= P.nout) return;
     const int64_t k = P.k_base + kl;
     const R *__restrict__ taps;
@@ -102,12 +108,13 @@ __global__ void __launch_bounds__(256) k_generic(const GenParams P) {
     // taps i in [0, ih) read history, [ih, T) read x
     int64_t ihl = H - n;
     const int ih = (int)(ihl < 0 ? 0 : (ihl > T ? T : ihl));
-    for (int64_t c = blockIdx.y; c < P.nch; c += gridDim.y) {
+    for (int64_t c = (int64_t)blockIdx.y * cpb + cl; c < P.nch; c += (int64_t)gridDim.y * cpb) {
         const RX *__restrict__ xc = static_cast<const RX *>(P.x) + c * P.ldx * NC;
         const RX *__restrict__ hc = static_cast<const RX *>(P.hist) + c * H * NC;
         R acc[NC], dacc[NC];
 #pragma unroll
         for (int q = 0; q < NC; ++q) acc[q] = dacc[q] = R(0);
+#pragma unroll 4
         for (int i = 0; i < ih; ++i) {
             RX s[NC];
             ld_sample<RX, NC>(hc, n + i, s);
@@ -148,6 +155,43 @@ __global__ void __launch_bounds__(256) k_generic(const GenParams P) {
         }
         st_sample<R, NC>(static_cast<R *>(P.y) + c * P.ldy * NC, k, acc);
     }
+}
+
+// Chunk heads of long filters (integer schedules): the few outputs whose window reaches the history, for every channel.
+// With one thread per output a warp's loads are T-strided and each lane walks its whole window alone (decimator 1//8 x
+// 256 taps, 1024 channels: 31 us for 40 outputs per channel, 14 % of the step).  Here a WARP computes one output of one
+// channel: lane i takes taps i, i+32, ... (consecutive lanes read consecutive samples and taps), then a shuffle tree.
+template <typename RX, typename R, int NC>
+__global__ void __launch_bounds__(256) k_head_warp(const GenParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;            // (channel, output) pair of this warp
+    if (w >= P.nout * P.nch) return;
+    const int64_t c = w / P.nout, kl = w - c * P.nout;
+    const int64_t k = P.k_base + kl;
+    const int64_t t = P.p0 + k * P.M;
+    const int64_t tq = t / P.L, tr = t - tq * P.L;
+    const int64_t n = P.d0m1 + tq, H = P.H;
+    const int T = (int)P.T;
+    const R *__restrict__ taps = static_cast<const R *>(P.bank) + tr * P.T;
+    const RX *__restrict__ hc = static_cast<const RX *>(P.hist) + c * H * NC;
+    const RX *__restrict__ xw = static_cast<const RX *>(P.x) + (c * P.ldx + (n - H)) * NC;
+    R acc[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) acc[q] = R(0);
+#pragma unroll 4
+    for (int i = lane; i < T; i += 32) {
+        RX s[NC];
+        if (n + i < H) ld_sample<RX, NC>(hc, n + i, s);
+        else ld_sample<RX, NC>(xw, i, s);
+        const R tv = __ldg(taps + i);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) acc[q] = fma(tv, (R)s[q], acc[q]);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    if (lane == 0) st_sample<R, NC>(static_cast<R *>(P.y) + c * P.ldy * NC, k, acc);
 }
 
 // Integer schedules (standard / interpolator / decimator / rational) that no tiled kernel covers -- few channels,
