@@ -343,18 +343,45 @@ static int64_t replay_table(const mrb_filter *f, int64_t n_in, mrb_state *end, s
         s.input_deficit -= n_in;
     } else {
         ArbState a{s.phi_accumulator, s.input_deficit};                 // xIdx = inputDeficit, :715,:812
-        while (a.xIdx <= n_in) {
-            if (vn) vn->push_back(a.xIdx - 1);
-            if (f->kind == MRB_ARBITRARY) {
-                if (vphi) vphi->push_back((int32_t)(s.phi_idx - 1));
-                if (va) va->push_back(s.alpha);
-            } else if (va) {
-                va->push_back(a.acc);                                   // Float64 phiIdx the taps are evaluated at
+        const bool arb = f->kind == MRB_ARBITRARY;
+        if (vn) {
+            // schedule wanted: write through raw pointers into storage sized for the bound of outputlength (:375-381)
+            // plus slack, grown if the loop decides otherwise (push_back and its capacity checks cost as much as the
+            // recurrence itself)
+            size_t cap = (size_t)((double)(n_in - s.input_deficit + 1) * f->rate) + 16;
+            vn->resize(cap); if (va) va->resize(cap); if (vphi && arb) vphi->resize(cap);
+            int64_t *pn = vn->data(); double *pa = va ? va->data() : nullptr; int32_t *pp = (vphi && arb) ? vphi->data() : nullptr;
+            size_t c = 0;
+            while (a.xIdx <= n_in) {
+                if (c == cap) {
+                    cap += cap / 2 + 16;
+                    vn->resize(cap); pn = vn->data();
+                    if (pa) { va->resize(cap); pa = va->data(); }
+                    if (pp) { vphi->resize(cap); pp = vphi->data(); }
+                }
+                pn[c] = a.xIdx - 1;
+                if (arb) {
+                    if (pp) pp[c] = (int32_t)(s.phi_idx - 1);
+                    if (pa) pa[c] = s.alpha;
+                } else if (pa) {
+                    pa[c] = a.acc;                                      // Float64 phiIdx the taps are evaluated at
+                }
+                ++c;
+                arb_update(a, f->delta, f->Nphi);
+                if (arb) {
+                    s.phi_idx = (int64_t)a.acc;                         // floor of a value >= 1, :671-672
+                    s.alpha = a.acc - (double)s.phi_idx;
+                }
             }
-            ++count;
-            arb_update(a, f->delta, f->Nphi);
-            if (f->kind == MRB_ARBITRARY) {
-                s.phi_idx = (int64_t)std::floor(a.acc);                 // :671-672
+            vn->resize(c); if (pa) va->resize(c); if (pp) vphi->resize(c);
+            count = (int64_t)c;
+        } else {
+            while (a.xIdx <= n_in) {
+                ++count;
+                arb_update(a, f->delta, f->Nphi);
+            }
+            if (arb && count > 0) {
+                s.phi_idx = (int64_t)a.acc;
                 s.alpha = a.acc - (double)s.phi_idx;
             }
         }
@@ -728,11 +755,12 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                     P.mode = SEQ_ARBITRARY;
                 } else {
                     P.mode = SEQ_FARROW; P.taptab = f->d_taptab;
-                    const unsigned g = (unsigned)ceil_div(cnt * f->T, 256);
+                    // tap rows for the outputs the generic kernel computes: the whole slice, or only its head
+                    const unsigned g = (unsigned)ceil_div(P.nout * f->T, 256);
                     if (is_double(f->ty))
-                        k_farrow_taps<double><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, cnt, (double *)f->d_taptab, f->th == MRB_F32);
+                        k_farrow_taps<double><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, P.nout, (double *)f->d_taptab, f->th == MRB_F32);
                     else
-                        k_farrow_taps<float><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, cnt, (float *)f->d_taptab, f->th == MRB_F32);
+                        k_farrow_taps<float><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, P.nout, (float *)f->d_taptab, f->th == MRB_F32);
                     ++f->launches;
                 }
                 dispatch_generic(f, P, st);

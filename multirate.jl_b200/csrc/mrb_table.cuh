@@ -65,35 +65,37 @@ k_table_rows(const R *__restrict__ pfb, const R *__restrict__ dpfb, const double
              int rowlen, int farrow, int tap_is_f32, const int64_t *__restrict__ sn, const int32_t *__restrict__ sphi,
              const double *__restrict__ sa, int64_t H, int64_t nout, R *__restrict__ rows, int32_t *__restrict__ astart,
              int A) {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= nout * rowlen) return;
-    const int64_t k = idx / rowlen;
-    const int j = (int)(idx - k * rowlen);
+    // one warp per output row (8 rows per block): the row's schedule entries are read once, no index division
+    const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= nout) return;
+    const int lane = threadIdx.x & 31;
     // the kTabGroup outputs of a group read ONE register window that starts at the aligned window start of the
     // group's first output; every row of the group is shifted to its own place inside that window
     const int64_t xs = sn[k] - H;                                    // x index of the window start (may be < 0: head)
     const int64_t xg = sn[k / kTabGroup * kTabGroup] - H;
     const int64_t al = xg >= 0 ? xg / A * A : -((-xg + A - 1) / A) * A;
     const int d = (int)(xs - al);
-    if (j == 0) astart[k] = (int32_t)al;
-    const int i = j - d;
-    R v = R(0);
-    if (i >= 0 && i < T) {
-        if (farrow) {
-            // currentTaps[i] = polyval(pnfb[i], phase): Horner highest order first in Float64 with separately
-            // rounded multiply and add, rounded to the tap type (src/Filters.jl:789-791)
-            const double ph = sa[k];
-            const double *c = pnfb + (int64_t)i * P1;
-            double a = c[P1 - 1];
-            for (int p = P1 - 2; p >= 0; --p) a = __dadd_rn(__dmul_rn(a, ph), c[p]);
-            if (tap_is_f32) a = (double)(float)a;
-            v = (R)a;
-        } else {
-            const int64_t o = (int64_t)sphi[k] * T + i;
-            v = (R)((double)pfb[o] + sa[k] * (double)dpfb[o]);
+    if (lane == 0) astart[k] = (int32_t)al;
+    const double ph = sa[k];                                         // farrow: phase; arbitrary: alpha
+    const int64_t obase = farrow ? 0 : (int64_t)sphi[k] * T;
+    for (int j = lane; j < rowlen; j += 32) {
+        const int i = j - d;
+        R v = R(0);
+        if (i >= 0 && i < T) {
+            if (farrow) {
+                // currentTaps[i] = polyval(pnfb[i], phase): Horner highest order first in Float64 with separately
+                // rounded multiply and add, rounded to the tap type (src/Filters.jl:789-791)
+                const double *c = pnfb + (int64_t)i * P1;
+                double a = c[P1 - 1];
+                for (int p = P1 - 2; p >= 0; --p) a = __dadd_rn(__dmul_rn(a, ph), c[p]);
+                if (tap_is_f32) a = (double)(float)a;
+                v = (R)a;
+            } else {
+                v = (R)((double)pfb[obase + i] + ph * (double)dpfb[obase + i]);
+            }
         }
+        rows[k * rowlen + j] = v;
     }
-    rows[idx] = v;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -423,8 +425,7 @@ static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind,
     if (table_reserve(p, cnt) != cudaSuccess) return -2;
 
     {   // pre-pass: rows + aligned starts for the whole slice (the head rows are not used)
-        const int64_t total = cnt * p.rowlen;
-        const unsigned g = (unsigned)ceil_div(total, 256);
+        const unsigned g = (unsigned)ceil_div(cnt, 8);               // one warp per row
         if (p.K == TAB_F64)
             k_table_rows<double><<<g, 256, 0, st>>>((const double *)d_pfb, (const double *)d_dpfb, d_pnfb, P1, p.T, p.rowlen,
                                                     kind == 5, tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt,
