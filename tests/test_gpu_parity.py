@@ -456,6 +456,34 @@ def test_decimator_c64_kernel_shapes(M, ntaps, nch, tx, rng):
         assert any(k.startswith("decim_c64" if tx == np.complex64 else "decim_f32") for k in used), used
 
 
+@pytest.mark.parametrize("th,tx", [(np.float32, np.float32), (np.float32, np.complex64), (np.float64, np.float64),
+                                   (np.float64, np.complex128), (np.float64, np.complex64)])
+@pytest.mark.parametrize("M,ntaps,nch", [(8, 256, 40), (4, 77, 3), (16, 300, 1)])
+def test_head_kernel_short_chunks(th, tx, M, ntaps, nch, rng):
+    """k_head_warp (mrb_kernels.cuh): short launches of decimating filters with long windows -- chunk heads, and whole
+    chunks when they are short -- one warp per output and channel.  Every sample dtype pairing, chunks from one sample to
+    a few hundred outputs, state carried; against the oracle and k_generic."""
+    import torch
+    h = rng.standard_normal(ntaps).astype(th)
+    ratio = Fraction(1, M)
+    edges = [0, 1, 2, M + 3, 40 * M + 1, 41 * M, 300 * M + 5, 300 * M + 6, 420 * M]
+    x = rand_samples(rng, (nch, edges[-1]), tx)
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
+    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
+    g.set_kernel_policy(1)
+    o = mo.FIRFilter(h, ratio)
+    used = set()
+    for a, b in zip(edges[:-1], edges[1:]):
+        y, yg, w = f.filt(xd[:, a:b]).cpu().numpy(), g.filt(xd[:, a:b]).cpu().numpy(), o.filt(x[:, a:b])
+        assert y.shape == w.shape
+        assert nerr(y, w) <= tol_for(y.dtype) and nerr(yg, y) <= tol_for(y.dtype)
+        assert states_equal(f, o)
+        if y.shape[1]:
+            used.add(f.last_kernel)
+    assert "head" in used, used
+
+
 @pytest.mark.parametrize("ratio,ntaps", [(Fraction(147, 160), 3528), (Fraction(3, 17), 120), (Fraction(1, 1), 63),
                                          (Fraction(7, 1), 100), (Fraction(1, 5), 41), (Fraction(160, 147), 1600)])
 @pytest.mark.parametrize("th,tx,nch", [(np.float32, np.float32, 1), (np.float32, np.complex64, 3), (np.float64, np.float64, 2),
