@@ -161,9 +161,11 @@ int32_t mrb_launch_count(const mrb_filter *f, int64_t *n);
  * mean duration per mrb_filt call in milliseconds and the number of calls averaged, and clears the record. */
 int32_t mrb_set_timing(mrb_filter *f, int32_t on);
 int32_t mrb_get_timing(mrb_filter *f, double *mean_ms, int64_t *n_calls);
-/* select the kernel family: 0 = automatic (fast tiled kernels where applicable), 1 = force the generic kernel */
+/* select the kernel family: 0 = automatic (the tiled kernels, k_stream and k_head_warp where applicable),
+ * 1 = k_generic alone (the always-correct path the parity tests use as a second opinion) */
 int32_t mrb_set_kernel_policy(mrb_filter *f, int32_t policy);
-/* name of the kernel family used by the last mrb_filt on this handle ("generic", "tiled_s1", ...) */
+/* name of the kernel that computed the body of the last mrb_filt on this handle ("generic", "stream", "head",
+ * "tiled_c64_t24_r12", "unit_f32_l4_r8", "decim_c64_m8", "table_f32", ...; "none" before the first call) */
 const char *mrb_last_kernel(const mrb_filter *f);
 
 const char *mrb_last_error(void);

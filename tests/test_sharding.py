@@ -90,6 +90,28 @@ def test_segment_plan_against_oracle_stream():
             assert len(y) == cnt and np.allclose(y, whole[k0:k0 + cnt], rtol=0, atol=1e-12 * np.abs(whole).max())
 
 
+@pytest.mark.parametrize("polyorder", [None, 3])
+def test_segment_plan_table_kinds_against_oracle_stream(polyorder):
+    """SURVEY 8f rank 4 on the host: the plan of an arbitrary-rate / Farrow stream split (start states by exact replay)
+    tiles the single-stream output exactly, and a fresh oracle filter brought to n0 reproduces each segment."""
+    rng = np.random.default_rng(5)
+    N = 16
+    h = rng.random(N * 6)
+    for rate in (0.918734, 2.31, 1 / 3.7):
+        args = (h, rate, N) if polyorder is None else (h, rate, N, polyorder)
+        n = 6000
+        x = rng.random(n)
+        whole = mo.FIRFilter(*args).filt(x)
+        plan = mr.segment_plan(mr.FIRFilter(*args), n, 4)
+        assert plan[0][2] == 0 and plan[-1][2] + plan[-1][3] == len(whole)
+        assert all(a[2] + a[3] == b[2] for a, b in zip(plan, plan[1:]))
+        for n0, n1, k0, cnt in plan:
+            o = mo.FIRFilter(*args)
+            o.filt(x[:n0])
+            y = o.filt(x[n0:n1])
+            assert len(y) == cnt and np.array_equal(y, whole[k0:k0 + cnt])
+
+
 @pytest.mark.parametrize("n,w", [(10, 3), (65536, 8), (7, 8), (0, 2)])
 def test_channel_shard_tiles(n, w):
     blocks = [mr.channel_shard(n, w, r) for r in range(w)]
