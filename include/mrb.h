@@ -122,6 +122,11 @@ int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ld_x, int64_t n_in, 
 /* Advance the state machine as if n_in samples had been filtered, without data (host only).
  * History is NOT updated.  Used to run the data-independent sequencing ahead / on host-only handles. */
 int32_t mrb_advance(mrb_filter *f, int64_t n_in, int64_t *n_out);
+/* The schedule the next n_in inputs will produce, state untouched: per output the 0-based index of the last input
+ * sample of its window (the loops' inputIdx / xIdx minus one, src/Filters.jl:558-569, 613-625, 717-732, 814-826), the
+ * 0-based polyphase branch, and alpha (arbitrary, :671-672) or the Float64 phase the taps are evaluated at (farrow,
+ * :789).  Destinations may be NULL; each holds mrb_output_count(n_in) entries.  For output time bases and tests. */
+int32_t mrb_get_schedule(mrb_filter *f, int64_t n_in, int64_t *n_idx, int32_t *branch, double *frac);
 
 /* reset(self): src/Filters.jl:244-260 (defined here as full re-initialisation) */
 int32_t mrb_reset(mrb_filter *f);

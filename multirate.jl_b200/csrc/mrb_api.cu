@@ -341,6 +341,9 @@ static int64_t replay_table(const mrb_filter *f, int64_t n_in, mrb_state *end, s
     int64_t count = 0;
     if (n_in < s.input_deficit) {                                       // :705-709, :805-809
         s.input_deficit -= n_in;
+        if (vn) vn->clear();
+        if (va) va->clear();
+        if (vphi) vphi->clear();
     } else {
         ArbState a{s.phi_accumulator, s.input_deficit};                 // xIdx = inputDeficit, :715,:812
         const bool arb = f->kind == MRB_ARBITRARY;
@@ -352,6 +355,8 @@ static int64_t replay_table(const mrb_filter *f, int64_t n_in, mrb_state *end, s
             vn->resize(cap); if (va) va->resize(cap); if (vphi && arb) vphi->resize(cap);
             int64_t *pn = vn->data(); double *pa = va ? va->data() : nullptr; int32_t *pp = (vphi && arb) ? vphi->data() : nullptr;
             size_t c = 0;
+            const int64_t phi0 = s.phi_idx;
+            const double alpha0 = s.alpha;
             while (a.xIdx <= n_in) {
                 if (c == cap) {
                     cap += cap / 2 + 16;
@@ -360,18 +365,29 @@ static int64_t replay_table(const mrb_filter *f, int64_t n_in, mrb_state *end, s
                     if (pp) { vphi->resize(cap); pp = vphi->data(); }
                 }
                 pn[c] = a.xIdx - 1;
-                if (arb) {
-                    if (pp) pp[c] = (int32_t)(s.phi_idx - 1);
-                    if (pa) pa[c] = s.alpha;
-                } else if (pa) {
-                    pa[c] = a.acc;                                      // Float64 phiIdx the taps are evaluated at
-                }
+                if (pa) pa[c] = a.acc;       // farrow: the Float64 phiIdx the taps are evaluated at; arbitrary: split below
                 ++c;
                 arb_update(a, f->delta, f->Nphi);
-                if (arb) {
-                    s.phi_idx = (int64_t)a.acc;                         // floor of a value >= 1, :671-672
-                    s.alpha = a.acc - (double)s.phi_idx;
+            }
+            if (arb) {
+                // branch and alpha of every output from the accumulator it started with (:671-672) -- outside the
+                // sequential loop, where the conversion vectorises.  Output 0 keeps the carried pair: setphase may
+                // have clamped it.
+                if (c > 0) {
+                    if (pp) pp[0] = (int32_t)(phi0 - 1);
+                    if (pa) pa[0] = alpha0;
                 }
+                if (pa && pp) {
+                    for (size_t i = 1; i < c; ++i) {
+                        const int32_t ph = (int32_t)pa[i];              // floor of a value in [1, Nphi+1)
+                        pp[i] = ph - 1;
+                        pa[i] -= (double)ph;
+                    }
+                } else if (pa) {
+                    for (size_t i = 1; i < c; ++i) pa[i] -= (double)(int32_t)pa[i];
+                }
+                s.phi_idx = (int64_t)a.acc;
+                s.alpha = a.acc - (double)s.phi_idx;
             }
             vn->resize(c); if (pa) va->resize(c); if (pp) vphi->resize(c);
             count = (int64_t)c;
@@ -397,7 +413,7 @@ static int64_t replay_table(const mrb_filter *f, int64_t n_in, mrb_state *end, s
 static int64_t replay_cached(mrb_filter *f, int64_t n_in, mrb_state *end) {
     const mrb_state from{f->phiIdx, f->deficit, f->xIdx, f->acc, f->alpha};
     if (!(f->sched_valid && f->sched_n_in == n_in && memcmp(&from, &f->sched_from, sizeof from) == 0)) {
-        f->vn.clear(); f->vphi.clear(); f->va.clear();
+        // (the vectors keep their size from the previous call: growing them by a few elements initialises only those)
         f->sched_count = replay_table(f, n_in, &f->sched_end, &f->vn, f->kind == MRB_ARBITRARY ? &f->vphi : nullptr, &f->va);
         f->sched_from = from; f->sched_n_in = n_in; f->sched_valid = true;
     }
@@ -422,6 +438,33 @@ extern "C" int32_t mrb_output_count(const mrb_filter *f, int64_t n_in, int64_t *
 
 static void commit_state(mrb_filter *f, const mrb_state &s) {
     f->phiIdx = s.phi_idx; f->deficit = s.input_deficit; f->xIdx = s.x_idx; f->acc = s.phi_accumulator; f->alpha = s.alpha;
+}
+
+// The schedule the next n_in inputs will produce, without advancing the state: per output the 0-based index of the
+// window's last input sample, and for the arbitrary-rate kinds the 0-based branch (arbitrary) and alpha (arbitrary) or
+// Float64 phase (farrow).  Any of the three destinations may be NULL; each must hold mrb_output_count(n_in) entries.
+extern "C" int32_t mrb_get_schedule(mrb_filter *f, int64_t n_in, int64_t *n_idx, int32_t *branch, double *frac) {
+    if (!f || n_in < 0) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    if (is_table_kind(f)) {
+        const int64_t N = replay_cached(f, n_in, nullptr);
+        if (N == 0) return MRB_OK;
+        if (n_idx) memcpy(n_idx, f->vn.data(), (size_t)N * sizeof(int64_t));
+        if (frac) memcpy(frac, f->va.data(), (size_t)N * sizeof(double));
+        if (branch) {
+            if (f->kind == MRB_ARBITRARY) memcpy(branch, f->vphi.data(), (size_t)N * sizeof(int32_t));
+            else for (int64_t k = 0; k < N; ++k) branch[k] = (int32_t)f->va[k] - 1;
+        }
+        return MRB_OK;
+    }
+    const int64_t p = f->phiIdx - 1, d = f->deficit;
+    const int64_t N = IntSeq::count(f->L, f->M, p, d, n_in);
+    for (int64_t k = 0; k < N; ++k) {                                    // closed form of :558-569, :613-625
+        const int64_t t = p + k * f->M;
+        if (n_idx) n_idx[k] = d - 1 + t / f->L;
+        if (branch) branch[k] = (int32_t)(t % f->L);
+        if (frac) frac[k] = 0.0;
+    }
+    return MRB_OK;
 }
 
 extern "C" int32_t mrb_advance(mrb_filter *f, int64_t n_in, int64_t *n_out) {

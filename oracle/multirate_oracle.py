@@ -329,6 +329,7 @@ class FIRFilter:
                 n_idx.append(inputIdx)
                 inputIdx += k.decimation
             k.inputDeficit = inputIdx - xLen
+            self.last_schedule = (n_idx, [1] * len(n_idx))
             y = self._dots(np.repeat(k.h[:, None], len(n_idx), axis=1), x2, n_idx)
             self.history = shiftin(self.history, x2)
             return self._finish(y)
@@ -346,6 +347,7 @@ class FIRFilter:
                 inputIdx += int(math.floor((k.phiIdx + decimation - 1) / interpolation))   # :567
                 k.phiIdx = nextphase(k.phiIdx, k.ratio)                                    # :568
             k.inputDeficit = inputIdx - xLen
+            self.last_schedule = (n_idx, phis)
             y = self._dots(k.pfb[:, np.asarray(phis, dtype=np.int64) - 1], x2, n_idx)
             self.history = shiftin(self.history, x2)
             return self._finish(y)

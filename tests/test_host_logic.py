@@ -194,3 +194,38 @@ def test_set_taps_rebuilds_banks_and_keeps_state(rng):
             f.set_taps(h2[:-1])
         with pytest.raises(mr.MrbError):
             F.check(F.lib().mrb_set_taps(f._handle, h2.ctypes.data, 49, None))
+
+
+def product_schedule(f, n_in):
+    N = C.c_int64()
+    F.check(F.lib().mrb_output_count(f._handle, n_in, C.byref(N)))
+    n, b, a = np.empty(N.value, np.int64), np.empty(N.value, np.int32), np.empty(N.value, np.float64)
+    F.check(F.lib().mrb_get_schedule(f._handle, n_in, n.ctypes.data, b.ctypes.data, a.ctypes.data))
+    return n, b, a
+
+
+@pytest.mark.parametrize("args", [(Fraction(147, 160),), (Fraction(3, 17),), (Fraction(17, 3),), (Fraction(1, 8),),
+                                  (0.918734, 32), (1.37, 32), (1 / 2.123456789, 16), (0.918734, 32, 4), (3.3, 8, 2)])
+def test_schedule_bit_exact_against_the_oracle_loops(args, rng):
+    """PHASE sequencing, output by output: mrb_get_schedule (what the kernels are fed) == the literal loops of the
+    oracle (src/Filters.jl:558-569, 613-625, 717-732, 814-826) -- window positions, branches and the Float64 alpha /
+    phase bit for bit, over ragged chunks with carried state, a setphase in between for the kinds that have one."""
+    h = rng.random(32 * 9)
+    f = mr.FIRFilter(h, *args, nchannels=1, sample_dtype=np.float64, device=-1)
+    o = mo.FIRFilter(h, *args)
+    for i, n in enumerate([1, 2, 700, 3, 4096, 0, 1531, 65536]):
+        if i == 4 and not (len(args) == 1 and args[0].numerator == 1):
+            assert f.setphase(0.37) == o.setphase(0.37)
+        pn, pb, pa = product_schedule(f, n)
+        advance(f, n)
+        o.last_schedule = ([], [], [])
+        y = o.filt(np.zeros(n))
+        sched = o.last_schedule
+        assert len(pn) == len(y) == len(sched[0])
+        assert np.array_equal(pn, np.asarray(sched[0], dtype=np.int64) - 1)
+        if len(args) == 3:                                       # farrow: Float64 phase
+            assert np.array_equal(pa, np.asarray(sched[1], dtype=np.float64))
+        else:
+            assert np.array_equal(pb, np.asarray(sched[1], dtype=np.int64) - 1)
+            if len(args) == 2:                                   # arbitrary: alpha
+                assert np.array_equal(pa, np.asarray(sched[2], dtype=np.float64))
