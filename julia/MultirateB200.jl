@@ -165,6 +165,16 @@ function seek!(f::FIRFilter, n0::Integer, halo::Ptr{Cvoid}=C_NULL, ldhalo::Integ
     check(ccall((:mrb_seek, libmrb), Int32, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Ref{Int64}, Ptr{Cvoid}),
                 hosthandle(f), n0, halo, ldhalo, k0, stream)); k0[]
 end
+# per-output schedule of the next `n` inputs, state untouched: (0-based index of each window's last input sample,
+# 0-based branch, α or Farrow phase) -- the loop variables of src/Filters.jl:558-569, 613-625, 717-732, 814-826
+function schedule(f::FIRFilter, n::Integer)
+    cnt = Ref{Int64}(0)
+    check(ccall((:mrb_output_count, libmrb), Int32, (Ptr{Cvoid}, Int64, Ref{Int64}), hosthandle(f), n, cnt))
+    idx = Vector{Int64}(undef, cnt[]); branch = Vector{Int32}(undef, cnt[]); frac = Vector{Float64}(undef, cnt[])
+    check(ccall((:mrb_get_schedule, libmrb), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}),
+                hosthandle(f), n, idx, branch, frac))
+    idx, branch, frac
+end
 # live tap update (no upstream counterpart): same tap count, phase state and history kept; Farrow filters pass the
 # refitted coefficients (pfb2pnfb of the new taps, T x (order+1), row-major)
 function settaps!(f::FIRFilter{Tk,Th}, h::Vector{Th}, polycoeffs::Union{Nothing,Vector{Float64}}=nothing) where {Tk,Th}
