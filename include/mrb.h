@@ -116,9 +116,14 @@ int32_t mrb_taps2pfb(const void *h, int64_t h_len, int32_t dtype, int64_t n_phi,
  * `stream` (a cudaStream_t; NULL = default stream); the count is computed on the host. */
 int32_t mrb_filt(mrb_filter *f, const void *x, int64_t ld_x, int64_t n_in, void *y, int64_t ld_y,
                  int64_t y_capacity, int64_t *n_out, void *stream);
-/* Same call with HOST pointers: stages through device buffers owned by the handle, synchronous. */
+/* Same call with HOST pointers: stages through device buffers owned by the handle, synchronous.  Channel blocks
+ * are pipelined H2D -> kernels -> D2H over several streams; every stream owns the schedule / tap-row buffers it
+ * writes, so concurrently running blocks never share mutable state. */
 int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ld_x, int64_t n_in, void *y, int64_t ld_y,
                       int64_t y_capacity, int64_t *n_out);
+/* Shape of that pipeline: input bytes per channel block (MiB) and number of streams (1..4); 0 keeps the default
+ * (64 MiB, 2 streams, or the MRB_HOST_BLOCK_MIB / MRB_HOST_STREAMS environment variables). */
+int32_t mrb_set_host_pipeline(mrb_filter *f, int32_t block_mib, int32_t n_streams);
 /* Advance the state machine as if n_in samples had been filtered, without data (host only).
  * History is NOT updated.  Used to run the data-independent sequencing ahead / on host-only handles. */
 int32_t mrb_advance(mrb_filter *f, int64_t n_in, int64_t *n_out);

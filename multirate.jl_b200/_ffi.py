@@ -26,7 +26,7 @@ F32, F64, C64, C128 = 0, 1, 2, 3
 
 # every symbol include/mrb.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = ["mrb_create", "mrb_destroy", "mrb_get_info", "mrb_outputlength", "mrb_output_count", "mrb_inputlength",
-           "mrb_nextphase", "mrb_taps2pfb", "mrb_filt", "mrb_filt_host", "mrb_advance", "mrb_reset", "mrb_setphase",
+           "mrb_nextphase", "mrb_taps2pfb", "mrb_filt", "mrb_filt_host", "mrb_set_host_pipeline", "mrb_advance", "mrb_reset", "mrb_setphase",
            "mrb_get_state", "mrb_set_state", "mrb_get_history", "mrb_set_history", "mrb_tapsforphase", "mrb_get_pfb",
            "mrb_seek", "mrb_get_schedule", "mrb_set_taps", "mrb_launch_count", "mrb_set_timing", "mrb_get_timing", "mrb_set_kernel_policy", "mrb_last_kernel", "mrb_last_error", "mrb_version"]
 
@@ -93,6 +93,7 @@ def lib():
         "mrb_taps2pfb": (i32, [vp, i64, i32, i64, vp]),
         "mrb_filt": (i32, [vp, vp, i64, i64, vp, i64, i64, P(i64), vp]),
         "mrb_filt_host": (i32, [vp, vp, i64, i64, vp, i64, i64, P(i64)]),
+        "mrb_set_host_pipeline": (i32, [vp, i32, i32]),
         "mrb_advance": (i32, [vp, i64, P(i64)]), "mrb_reset": (i32, [vp]), "mrb_setphase": (i32, [vp, dbl]),
         "mrb_get_state": (i32, [vp, P(State)]), "mrb_set_state": (i32, [vp, P(State)]),
         "mrb_get_history": (i32, [vp, vp]), "mrb_set_history": (i32, [vp, vp]),

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -65,6 +66,33 @@ struct SchedSlot {            // pinned host staging + device copy of one table-
     bool pending = false;
 };
 
+// Everything run_channels WRITES on the device for the arbitrary-rate kinds: the uploaded schedule slices, the Farrow tap
+// table of the generic path and the per-output tap rows of the table kernel.  One context per pipeline stream of
+// mrb_filt_host (context 0 also serves mrb_filt): channel blocks that run concurrently on different streams never share
+// a buffer, and inside one stream the stream order keeps a slice's readers ahead of the next slice's writers.
+struct TableCtx {
+    SchedSlot slot[2];
+    bool ready = false;
+    void *d_taptab = nullptr;          // farrow: R[kSchedChunk][T]
+    TabRows rows;                      // table kernel: tap rows + aligned window starts of one slice
+};
+constexpr int kMaxHostStreams = 4;
+
+struct DeviceGuard {                   // the API leaves the caller's current device as it found it
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
+struct mrb_filter;
+static void free_device(mrb_filter *f);
+
 struct mrb_filter {
     int kind, th, tx, ty, device;
     int64_t hLen, L, M, Nphi, T, H, nch;
@@ -80,14 +108,17 @@ struct mrb_filter {
     double *d_pnfb = nullptr;
     void *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
-    SchedSlot slot[2];
-    int64_t sched_cap = 0;
-    void *d_taptab = nullptr;          // farrow: R[sched_cap][T]
+    TableCtx tctx[kMaxHostStreams];
     // host-call staging
     void *d_xs = nullptr, *d_ys = nullptr;
     size_t xs_bytes = 0, ys_bytes = 0;
     cudaStream_t own_stream = nullptr;
-    cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};   // further streams of the mrb_filt_host pipeline
+    cudaStream_t host_streams[kMaxHostStreams - 1] = {};          // further streams of the mrb_filt_host pipeline
+    // stream of the last asynchronous call: a call on ANOTHER stream first waits (on the device) for that work, so the
+    // history / schedule buffers of the handle are never read and written concurrently
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false;
+    cudaEvent_t order_ev = nullptr;
     // table kinds: the schedule of the call in flight.  The exact replay costs ~0.3 ms per 60 K outputs, and a caller
     // typically asks for the count (to size its buffer) right before it filters: the last replay is cached, keyed by
     // the state it started from and the input length.
@@ -100,26 +131,38 @@ struct mrb_filter {
     DecPlan decim;                     // fast path for complex64 decimators (mrb_decim.cuh)
     TabPlan table;                     // fast path for arbitrary / farrow on real samples (mrb_table.cuh)
     int policy = 0;
+    int host_block_mib = 0, host_streams_n = 0;   // mrb_set_host_pipeline; 0 = MRB_HOST_BLOCK_MIB / MRB_HOST_STREAMS / default
     int num_sms = 148;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // one pair per timed mrb_filt
     const char *last_kernel = "none";
     int64_t launches = 0;
+    mrb_filter() = default;
+    mrb_filter(const mrb_filter &) = delete;
+    mrb_filter &operator=(const mrb_filter &) = delete;
+    ~mrb_filter() { free_device(this); }   // every failure path of mrb_create / mrb_set_taps releases what was allocated
 };
 
 static const int64_t kSchedChunk = 1 << 16;   // outputs per table-schedule sub-chunk
 
 static void free_device(mrb_filter *f) {
     if (f->device < 0) return;
-    cudaSetDevice(f->device);
+    DeviceGuard guard(f->device);
     cudaFree(f->d_bank); cudaFree(f->d_dbank); cudaFree(f->d_pnfb);
     cudaFree(f->d_hist[0]); cudaFree(f->d_hist[1]);
-    for (auto &s : f->slot) {
-        cudaFreeHost(s.h_n); cudaFreeHost(s.h_phi); cudaFreeHost(s.h_a);
-        cudaFree(s.d_n); cudaFree(s.d_phi); cudaFree(s.d_a);
-        if (s.ev) cudaEventDestroy(s.ev);
+    for (auto &c : f->tctx) {
+        for (auto &s : c.slot) {
+            cudaFreeHost(s.h_n); cudaFreeHost(s.h_phi); cudaFreeHost(s.h_a);
+            cudaFree(s.d_n); cudaFree(s.d_phi); cudaFree(s.d_a);
+            if (s.ev) cudaEventDestroy(s.ev);
+            s = SchedSlot{};
+        }
+        cudaFree(c.d_taptab); c.d_taptab = nullptr;
+        tabrows_release(c.rows);
+        c.ready = false;
     }
-    cudaFree(f->d_taptab); cudaFree(f->d_xs); cudaFree(f->d_ys);
+    cudaFree(f->d_xs); cudaFree(f->d_ys);
+    if (f->order_ev) cudaEventDestroy(f->order_ev);
     tiled_release(f->tiled);
     unit_release(f->unit);
     decim_release(f->decim);
@@ -219,7 +262,7 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
         int ndev = 0;
         CU(cudaGetDeviceCount(&ndev));
         if (f->device >= ndev) return fail(MRB_ERR_NO_DEVICE, "device %d not present (%d devices)", f->device, ndev);
-        CU(cudaSetDevice(f->device));
+        DeviceGuard guard(f->device);
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, f->device));
         if (prop.major != 10)
@@ -275,7 +318,7 @@ extern "C" int32_t mrb_set_taps(mrb_filter *f, const void *hv, int64_t h_len, co
     if (f->kind == MRB_FARROW) f->pnfb.assign(poly_coeffs, poly_coeffs + f->T * (f->polyorder + 1));
     if (f->device < 0) return MRB_OK;
 
-    CU(cudaSetDevice(f->device));
+    DeviceGuard guard(f->device);
     CU(cudaDeviceSynchronize());                       // kernels in flight still read the old banks
     const bool dbl = is_double(f->ty);
     auto refresh = [&](const std::vector<double> &src, void *dst) -> cudaError_t {
@@ -300,9 +343,7 @@ extern "C" int32_t mrb_set_taps(mrb_filter *f, const void *hv, int64_t h_len, co
 }
 
 extern "C" int32_t mrb_destroy(mrb_filter *f) {
-    if (!f) return MRB_OK;
-    free_device(f);
-    delete f;
+    delete f;                                              // ~mrb_filter releases the device side
     return MRB_OK;
 }
 
@@ -509,7 +550,7 @@ extern "C" int32_t mrb_reset(mrb_filter *f) {
     if (!f) return fail(MRB_ERR_BAD_ARGUMENT, "null handle");
     init_state(f);
     if (f->device >= 0) {
-        CU(cudaSetDevice(f->device));
+        DeviceGuard guard(f->device);
         const size_t hb = (size_t)(f->H * f->nch) * dsize(f->tx);
         CU(cudaDeviceSynchronize());
         if (hb) CU(cudaMemset(f->d_hist[f->cur], 0, hb));
@@ -549,7 +590,9 @@ extern "C" int32_t mrb_set_state(mrb_filter *f, const mrb_state *s) {
     const int64_t maxphi = is_table_kind(f) ? f->Nphi : f->L;
     if (s->phi_idx < 1 || s->phi_idx > maxphi || s->input_deficit < 1)
         return fail(MRB_ERR_BAD_ARGUMENT, "state out of range");
-    if (is_table_kind(f) && !(s->phi_accumulator >= 1.0 && s->phi_accumulator < (double)(f->Nphi + 1)))
+    // closed upper bound: setphase(1.0) leaves the accumulator AT Nphi+1 (the next update wraps it), and a state read
+    // back from one handle must be accepted by another
+    if (is_table_kind(f) && !(s->phi_accumulator >= 1.0 && s->phi_accumulator <= (double)(f->Nphi + 1)))
         return fail(MRB_ERR_BAD_ARGUMENT, "phase accumulator out of range");
     commit_state(f, *s);
     return MRB_OK;
@@ -558,7 +601,7 @@ extern "C" int32_t mrb_set_state(mrb_filter *f, const mrb_state *s) {
 extern "C" int32_t mrb_get_history(mrb_filter *f, void *dst) {
     if (!f || !dst) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
     if (f->device < 0) return fail(MRB_ERR_NO_DEVICE, "host-only handle holds no history");
-    CU(cudaSetDevice(f->device));
+    DeviceGuard guard(f->device);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(dst, f->d_hist[f->cur], (size_t)(f->H * f->nch) * dsize(f->tx), cudaMemcpyDeviceToHost));
     return MRB_OK;
@@ -567,7 +610,7 @@ extern "C" int32_t mrb_get_history(mrb_filter *f, void *dst) {
 extern "C" int32_t mrb_set_history(mrb_filter *f, const void *src) {
     if (!f || !src) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
     if (f->device < 0) return fail(MRB_ERR_NO_DEVICE, "host-only handle holds no history");
-    CU(cudaSetDevice(f->device));
+    DeviceGuard guard(f->device);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(f->d_hist[f->cur], src, (size_t)(f->H * f->nch) * dsize(f->tx), cudaMemcpyHostToDevice));
     return MRB_OK;
@@ -631,12 +674,12 @@ static bool launch_stream(const GenParams &P, int num_sms, int device, cudaStrea
     const int64_t bytes = P.L * pitch * (int64_t)sizeof(R);
     if (P.mode != SEQ_INTEGER || P.nout < kStreamMinOutputs || bytes > kStreamMaxBankBytes || P.L >= (1ll << 31) / pitch)
         return false;
-    static bool attr_set[64] = {};                                     // per instantiation and device
-    if (device < 0 || device >= 64) return false;
-    if (!attr_set[device]) {
+    static std::atomic<bool> attr_set[64];                             // per instantiation and device; handles on
+    if (device < 0 || device >= 64) return false;                      // different threads may race here: setting the
+    if (!attr_set[device].load(std::memory_order_acquire)) {           // attribute twice is harmless, a torn flag is not
         if (cudaFuncSetAttribute(k_stream<RX, R, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamMaxBankBytes) != cudaSuccess)
             return false;
-        attr_set[device] = true;
+        attr_set[device].store(true, std::memory_order_release);
     }
     const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(8, (200 * 1024) / (bytes + 1024)));
     const int64_t target = per_sm * num_sms;
@@ -705,9 +748,9 @@ static void launch_history(const mrb_filter *f, const void *x, int64_t ldx, int6
     }
 }
 
-static int32_t ensure_sched(mrb_filter *f) {
-    if (f->sched_cap) return MRB_OK;
-    for (auto &s : f->slot) {
+static int32_t ensure_sched(mrb_filter *f, TableCtx &c) {
+    if (c.ready) return MRB_OK;
+    for (auto &s : c.slot) {
         CU(cudaMallocHost(&s.h_n, kSchedChunk * sizeof(int64_t)));
         CU(cudaMallocHost(&s.h_phi, kSchedChunk * sizeof(int32_t)));
         CU(cudaMallocHost(&s.h_a, kSchedChunk * sizeof(double)));
@@ -717,15 +760,27 @@ static int32_t ensure_sched(mrb_filter *f) {
         CU(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
     }
     if (f->kind == MRB_FARROW)
-        CU(cudaMalloc(&f->d_taptab, (size_t)kSchedChunk * f->T * (is_double(f->ty) ? 8 : 4)));
-    f->sched_cap = kSchedChunk;
+        CU(cudaMalloc(&c.d_taptab, (size_t)kSchedChunk * f->T * (is_double(f->ty) ? 8 : 4)));
+    c.ready = true;
+    return MRB_OK;
+}
+
+// A call on stream `st` must not overtake work the handle still has in flight on another stream (history double buffer,
+// schedule slices, tap rows): make `st` wait for it on the device.  No host synchronisation.
+static int32_t order_after_last(mrb_filter *f, cudaStream_t st) {
+    if (f->last_valid && f->last_stream != st) {
+        if (!f->order_ev) CU(cudaEventCreateWithFlags(&f->order_ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(f->order_ev, f->last_stream));
+        CU(cudaStreamWaitEvent(st, f->order_ev, 0));
+    }
     return MRB_OK;
 }
 
 // Filter channels [c0, c0+nc) of one chunk from the CURRENT handle state (not committed here).
 // x / y point at channel c0.  N = exact output count for this chunk.
+// `ctx` selects the table context (schedule slices, tap rows) this call may write: one per concurrently running stream.
 static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n_in, void *y, int64_t ldy, int64_t N,
-                            int64_t c0, int64_t nc, cudaStream_t st) {
+                            int64_t c0, int64_t nc, cudaStream_t st, int ctx) {
     const size_t es = dsize(f->tx);
     const char *hold = static_cast<const char *>(f->d_hist[f->cur]) + (size_t)(c0 * f->H) * es;
     char *hnew = static_cast<char *>(f->d_hist[f->cur ^ 1]) + (size_t)(c0 * f->H) * es;
@@ -755,7 +810,8 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 ++f->launches;
             }
         } else {
-            int32_t rc = ensure_sched(f);
+            TableCtx &tc = f->tctx[ctx];
+            int32_t rc = ensure_sched(f, tc);
             if (rc) return rc;
             // the exact host replay (data independent) was done by check_filt_args; uploaded in bounded sub-chunks
             const std::vector<int64_t> &vn = f->vn; const std::vector<int32_t> &vphi = f->vphi; const std::vector<double> &va = f->va;
@@ -763,7 +819,7 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
             int si = 0;
             for (int64_t k0 = 0; k0 < N; k0 += kSchedChunk, si ^= 1) {
                 const int64_t cnt = std::min(kSchedChunk, N - k0);
-                SchedSlot &s = f->slot[si];
+                SchedSlot &s = tc.slot[si];
                 if (s.pending) { CU(cudaEventSynchronize(s.ev)); s.pending = false; }
                 memcpy(s.h_n, vn.data() + k0, cnt * sizeof(int64_t));
                 memcpy(s.h_a, va.data() + k0, cnt * sizeof(double));
@@ -784,7 +840,7 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                     int64_t gspan = 0;                         // widest spread of window starts inside a group of 8 outputs
                     for (int64_t g0 = 0; g0 < cnt; g0 += kTabGroup)
                         gspan = std::max(gspan, vn[k0 + std::min(g0 + kTabGroup, cnt) - 1] - vn[k0 + g0]);
-                    const int64_t kb = table_try_launch(f->table, P, f->kind, f->polyorder + 1, f->th == MRB_F32, f->d_bank,
+                    const int64_t kb = table_try_launch(f->table, tc.rows, P, f->kind, f->polyorder + 1, f->th == MRB_F32, f->d_bank,
                                                         f->d_dbank, f->d_pnfb, f->rate, k0, cnt, head, gspan, st, &f->last_kernel,
                                                         &f->launches);
                     if (kb == -2) return fail(MRB_ERR_CUDA, "table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -797,13 +853,13 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 if (f->kind == MRB_ARBITRARY) {
                     P.mode = SEQ_ARBITRARY;
                 } else {
-                    P.mode = SEQ_FARROW; P.taptab = f->d_taptab;
+                    P.mode = SEQ_FARROW; P.taptab = tc.d_taptab;
                     // tap rows for the outputs the generic kernel computes: the whole slice, or only its head
                     const unsigned g = (unsigned)ceil_div(P.nout * f->T, 256);
                     if (is_double(f->ty))
-                        k_farrow_taps<double><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, P.nout, (double *)f->d_taptab, f->th == MRB_F32);
+                        k_farrow_taps<double><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, P.nout, (double *)tc.d_taptab, f->th == MRB_F32);
                     else
-                        k_farrow_taps<float><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, P.nout, (float *)f->d_taptab, f->th == MRB_F32);
+                        k_farrow_taps<float><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, P.nout, (float *)tc.d_taptab, f->th == MRB_F32);
                     ++f->launches;
                 }
                 dispatch_generic(f, P, st);
@@ -842,9 +898,12 @@ extern "C" int32_t mrb_filt(mrb_filter *f, const void *x, int64_t ldx, int64_t n
     mrb_state end;
     int32_t rc = check_filt_args(f, x, ldx, n_in, y, ldy, cap, &N, &end);
     if (rc) return rc;
-    CU(cudaSetDevice(f->device));
-    rc = run_channels(f, x, ldx, n_in, y, ldy, N, 0, f->nch, (cudaStream_t)stream);
+    DeviceGuard guard(f->device);
+    rc = order_after_last(f, (cudaStream_t)stream);
     if (rc) return rc;
+    rc = run_channels(f, x, ldx, n_in, y, ldy, N, 0, f->nch, (cudaStream_t)stream, 0);
+    if (rc) return rc;
+    f->last_stream = (cudaStream_t)stream; f->last_valid = true;
     commit_state(f, end);
     if (n_in > 0 && f->H > 0) f->cur ^= 1;
     if (n_out) *n_out = N;
@@ -868,12 +927,14 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
     mrb_state end;
     int32_t rc = check_filt_args(f, x, ldx, n_in, y, ldy, cap, &N, &end);
     if (rc) return rc;
-    CU(cudaSetDevice(f->device));
+    DeviceGuard guard(f->device);
     const size_t es = dsize(f->tx), eo = dsize(f->ty);
     // channel blocks of ~MRB_HOST_BLOCK_MIB (64) MiB of input, pipelined over MRB_HOST_STREAMS (1..4, default 2) streams
     // (measured: 16..256 MiB x 2..4 streams all land on the same 86 GB/s full-duplex PCIe limit)
-    static const int blk_mib = getenv("MRB_HOST_BLOCK_MIB") ? std::max(1, atoi(getenv("MRB_HOST_BLOCK_MIB"))) : 64;
-    static const int nst = getenv("MRB_HOST_STREAMS") ? std::min(4, std::max(1, atoi(getenv("MRB_HOST_STREAMS")))) : 2;
+    static const int env_mib = getenv("MRB_HOST_BLOCK_MIB") ? std::max(1, atoi(getenv("MRB_HOST_BLOCK_MIB"))) : 64;
+    static const int env_nst = getenv("MRB_HOST_STREAMS") ? std::min(kMaxHostStreams, std::max(1, atoi(getenv("MRB_HOST_STREAMS")))) : 2;
+    const int blk_mib = f->host_block_mib > 0 ? f->host_block_mib : env_mib;
+    const int nst = f->host_streams_n > 0 ? f->host_streams_n : env_nst;
     int64_t cb = std::max<int64_t>(1, (int64_t)(((size_t)blk_mib << 20) / std::max<size_t>(1, (size_t)n_in * es)));
     cb = std::min(cb, f->nch);
     // staging row pitches are multiples of 16 bytes, so the TMA fast paths apply whatever n_in and N are
@@ -882,11 +943,12 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
     const size_t xb = (size_t)cb * lxs * es, yb = (size_t)cb * lys * eo;
     rc = grow(&f->d_xs, &f->xs_bytes, nst * xb); if (rc) return rc;
     rc = grow(&f->d_ys, &f->ys_bytes, nst * yb); if (rc) return rc;
-    cudaStream_t sts[4] = {f->own_stream, nullptr, nullptr, nullptr};
+    cudaStream_t sts[kMaxHostStreams] = {f->own_stream};
     for (int i = 1; i < nst; ++i) {                        // the handle's own streams, on the handle's device
         if (!f->host_streams[i - 1]) CU(cudaStreamCreateWithFlags(&f->host_streams[i - 1], cudaStreamNonBlocking));
         sts[i] = f->host_streams[i - 1];
     }
+    for (int i = 0; i < nst; ++i) { rc = order_after_last(f, sts[i]); if (rc) return rc; }
     int b = 0;
     for (int64_t c0 = 0; c0 < f->nch; c0 += cb, b = (b + 1) % nst) {
         const int64_t nc = std::min(cb, f->nch - c0);
@@ -895,15 +957,16 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
         if (n_in > 0)
             CU(cudaMemcpy2DAsync(dx, (size_t)lxs * es, static_cast<const char *>(x) + (size_t)(c0 * ldx) * es,
                                  (size_t)ldx * es, (size_t)n_in * es, (size_t)nc, cudaMemcpyHostToDevice, st));
-        // (arbitrary / farrow: every block re-uploads the same schedule slices and rebuilds the same tap rows into the
-        // handle's buffers; blocks on other streams may be reading them meanwhile, but the bytes are identical)
-        rc = run_channels(f, dx, lxs, n_in, dy, lys, N, c0, nc, st);
+        // arbitrary / farrow: every block uploads the schedule slices and builds the tap rows it needs into the table
+        // context of ITS stream (TableCtx): blocks in flight on other streams never see these buffers change
+        rc = run_channels(f, dx, lxs, n_in, dy, lys, N, c0, nc, st, b);
         if (rc) return rc;
         if (N > 0)
             CU(cudaMemcpy2DAsync(static_cast<char *>(y) + (size_t)(c0 * ldy) * eo, (size_t)ldy * eo, dy, (size_t)lys * eo,
                                  (size_t)N * eo, (size_t)nc, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < nst; ++i) CU(cudaStreamSynchronize(sts[i]));
+    f->last_valid = false;                                 // nothing of this handle is in flight any more
     commit_state(f, end);
     if (n_in > 0 && f->H > 0) f->cur ^= 1;
     if (n_out) *n_out = N;
@@ -943,8 +1006,10 @@ extern "C" int32_t mrb_seek(mrb_filter *f, int64_t n0, const void *halo, int64_t
     }
     if (k0) *k0 = kk;
     if (f->device >= 0 && f->H > 0) {
-        CU(cudaSetDevice(f->device));
+        DeviceGuard guard(f->device);
         cudaStream_t st = (cudaStream_t)stream;
+        {   int32_t rc = order_after_last(f, st); if (rc) return rc; }
+        f->last_stream = st; f->last_valid = true;
         void *dst = f->d_hist[f->cur];
         if (!halo) {
             CU(cudaMemsetAsync(dst, 0, (size_t)(f->H * f->nch) * dsize(f->tx), st));
@@ -973,6 +1038,13 @@ extern "C" int32_t mrb_launch_count(const mrb_filter *f, int64_t *n) {
 extern "C" int32_t mrb_set_kernel_policy(mrb_filter *f, int32_t policy) {
     if (!f || policy < 0 || policy > 1) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
     f->policy = policy;
+    return MRB_OK;
+}
+
+extern "C" int32_t mrb_set_host_pipeline(mrb_filter *f, int32_t block_mib, int32_t n_streams) {
+    if (!f || block_mib < 0 || n_streams < 0 || n_streams > kMaxHostStreams) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    f->host_block_mib = block_mib;
+    f->host_streams_n = n_streams;
     return MRB_OK;
 }
 

@@ -317,6 +317,20 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
+// Device buffers one schedule slice's tap rows live in.  They are WRITTEN by every call (k_table_rows), so the
+// handle keeps one set per pipeline stream (mrb_api.cu TableCtx), not one per plan.
+struct TabRows {
+    void *d_rows = nullptr;            // Tap[slice outputs][rowlen]
+    int32_t *d_astart = nullptr;
+    int64_t cap = 0;                   // outputs the two buffers hold
+    int64_t row_bytes = 0;             // rowlen * tap bytes the buffers were sized for
+};
+
+static inline void tabrows_release(TabRows &r) {
+    cudaFree(r.d_rows); cudaFree(r.d_astart);
+    r = TabRows{};
+}
+
 struct TabPlan {
     bool ok = false;
     int K = TAB_F32;                   // sample kind the plan was built for
@@ -324,17 +338,12 @@ struct TabPlan {
     int T = 0, nblk = 0, rowlen = 0;
     TabParams *hp = nullptr;
     PFN_encodeTiled encode = nullptr;
-    void *d_rows = nullptr;            // Tap[slice outputs][rowlen]
-    int32_t *d_astart = nullptr;
-    int64_t cap = 0;                   // outputs the two buffers hold
     int num_sms = 148;
 };
 
 static inline void table_release(TabPlan &p) {
     delete p.hp;
     p.hp = nullptr;
-    cudaFree(p.d_rows); cudaFree(p.d_astart);
-    p.d_rows = nullptr; p.d_astart = nullptr;
     p.ok = false;
 }
 
@@ -389,23 +398,23 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
     return 0;
 }
 
-static inline cudaError_t table_reserve(TabPlan &p, int64_t nout) {
-    if (p.cap >= nout) return cudaSuccess;
-    cudaFree(p.d_rows); cudaFree(p.d_astart);
-    p.d_rows = nullptr; p.d_astart = nullptr; p.cap = 0;
+static inline cudaError_t table_reserve(const TabPlan &p, TabRows &r, int64_t nout) {
+    const int64_t rb = (int64_t)p.rowlen * p.ts;
+    if (r.cap >= nout && r.row_bytes == rb) return cudaSuccess;
+    tabrows_release(r);
     // two steps of slack: the kernel stages whole steps (32 rows) of the table
-    cudaError_t e = cudaMalloc(&p.d_rows, (size_t)(nout + 2 * kTabStep) * p.rowlen * p.ts);
+    cudaError_t e = cudaMalloc(&r.d_rows, (size_t)(nout + 2 * kTabStep) * (size_t)rb);
     if (e != cudaSuccess) return e;
-    e = cudaMalloc(&p.d_astart, (size_t)(nout + 2 * kTabStep) * sizeof(int32_t));
+    e = cudaMalloc(&r.d_astart, (size_t)(nout + 2 * kTabStep) * sizeof(int32_t));
     if (e != cudaSuccess) return e;
-    p.cap = nout;
+    r.cap = nout; r.row_bytes = rb;
     return cudaSuccess;
 }
 
 // One schedule slice: outputs [0, cnt) of the slice (y index y0 + k), of which the first `head` have windows that
 // reach into the history.  Builds the tap rows, then launches the main kernel for [k_begin, cnt).  Returns k_begin
 // (the caller computes the slice's outputs before it with the generic kernel), -1 when not covered, -2 on error.
-static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind, int P1, int tap_is_f32,
+static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams &G, int kind, int P1, int tap_is_f32,
                                        const void *d_pfb, const void *d_dpfb, const double *d_pnfb, double rate, int64_t y0, int64_t cnt,
                                        int64_t head, int64_t max_group_span, cudaStream_t st, const char **name, int64_t *launches) {
     static const bool trace = getenv("MRB_TRACE") != nullptr;
@@ -422,18 +431,18 @@ static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind,
     }
     const int64_t k_begin = (head + kTabStep - 1) / kTabStep * kTabStep;
     if (cnt - k_begin < 4 * kTabStep) MRB_TAB_SKIP("slice too short");
-    if (table_reserve(p, cnt) != cudaSuccess) return -2;
+    if (table_reserve(p, rw, cnt) != cudaSuccess) return -2;
 
     {   // pre-pass: rows + aligned starts for the whole slice (the head rows are not used)
         const unsigned g = (unsigned)ceil_div(cnt, 8);               // one warp per row
         if (p.K == TAB_F64)
             k_table_rows<double><<<g, 256, 0, st>>>((const double *)d_pfb, (const double *)d_dpfb, d_pnfb, P1, p.T, p.rowlen,
                                                     kind == 5, tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt,
-                                                    (double *)p.d_rows, p.d_astart, A);
+                                                    (double *)rw.d_rows, rw.d_astart, A);
         else
             k_table_rows<float><<<g, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, p.rowlen,
                                                    kind == 5, tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt,
-                                                   (float *)p.d_rows, p.d_astart, A);
+                                                   (float *)rw.d_rows, rw.d_astart, A);
         ++*launches;
     }
     TabParams &P = *p.hp;
@@ -464,14 +473,14 @@ static inline int64_t table_try_launch(TabPlan &p, const GenParams &G, int kind,
     const int smem = table_smem(p);
     const bool red = p.TB != (p.K == TAB_F32 ? TabCfg<TAB_F32>::TB : TabCfg<TAB_F64>::TB);
     if (p.K == TAB_F32) {
-        if (red) k_table_fir<TAB_F32, 88><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
-        else k_table_fir<TAB_F32, 96><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+        if (red) k_table_fir<TAB_F32, 88><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
+        else k_table_fir<TAB_F32, 96><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
     } else if (p.K == TAB_F64) {
-        if (red) k_table_fir<TAB_F64, 44><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)p.d_rows, p.d_astart, P);
-        else k_table_fir<TAB_F64, 48><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)p.d_rows, p.d_astart, P);
+        if (red) k_table_fir<TAB_F64, 44><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
+        else k_table_fir<TAB_F64, 48><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
     } else {
-        if (red) k_table_fir<TAB_C64, 44><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
-        else k_table_fir<TAB_C64, 48><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)p.d_rows, p.d_astart, P);
+        if (red) k_table_fir<TAB_C64, 44><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
+        else k_table_fir<TAB_C64, 48><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
     }
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
     *name = p.K == TAB_F32 ? "table_f32" : p.K == TAB_F64 ? "table_f64" : "table_c64";

