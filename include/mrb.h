@@ -69,10 +69,13 @@ typedef struct mrb_desc {
     double rate;           /* > 0 selects the arbitrary-rate constructors (:183,192); 0 selects the Rational one */
     int32_t n_phi;         /* arbitrary/farrow: number of polyphase branches (default 32, :183) */
     int32_t poly_order;    /* farrow: >= 0 ; arbitrary: -1 */
-    const double *poly_coeffs; /* farrow: taps_per_phase*(poly_order+1) host-fitted coefficients, row i =
+    const double *poly_coeffs; /* farrow: taps_per_phase*(poly_order+1) coefficients, row i =
                                   polyfit(pfb[i,:], order) lowest order first (src/Filters.jl:311-321,
-                                  src/support.jl:85-88).  The fit crosses the ABI as data because it is
-                                  ill-conditioned (cond ~ 1e6..1e8) and solver dependent. */
+                                  src/support.jl:85-88), or NULL = the library's own fit (mrb_pfb2pnfb).
+                                  The fit is ill-conditioned (cond ~ 1e6..1e8) and therefore solver dependent
+                                  (SVD and QR agree to ~1e-10 relative, not bit for bit): bindings should take
+                                  the coefficients from mrb_pfb2pnfb -- ONE recipe for every host language --
+                                  and may pass their own only to reproduce a particular reference build. */
     int64_t n_channels;
 } mrb_desc;
 
@@ -108,6 +111,13 @@ int32_t mrb_inputlength(int64_t n_out, int64_t interpolation, int64_t decimation
 int32_t mrb_nextphase(int64_t current_phase, int64_t interpolation, int64_t decimation, int64_t *next_phase);
 /* taps2pfb(h, Nphi): src/Filters.jl:284-298 ; pfb is column-major taps_per_phase x n_phi like the Julia Matrix */
 int32_t mrb_taps2pfb(const void *h, int64_t h_len, int32_t dtype, int64_t n_phi, void *pfb);
+
+/* pfb2pnfb(taps2pfb(h, Nphi), order): src/Filters.jl:311-321 with polyfit src/support.jl:85-88 -- the agreed recipe
+ * for the Farrow coefficients: per tap row i the least-squares polynomial through pfb[i, phi], phi = 1..Nphi, on the
+ * Vandermonde matrix A[phi, p] = phi^p solved by Householder QR in Float64 (what Julia's `A \ y` means for a full-rank
+ * rectangular A), coefficients lowest order first, rounded to the tap dtype (Poly{T}, :313) and returned as Float64:
+ * coeffs[i*(order+1) + p].  Host only. */
+int32_t mrb_pfb2pnfb(const void *h, int64_t h_len, int32_t dtype, int64_t n_phi, int32_t order, double *coeffs);
 
 /* filt!(buffer, self, x): src/Filters.jl:450-473 (standard), 489-517 (interpolator), 536-575 (rational),
  * 598-631 (decimator), 693-742 (arbitrary), 795-836 (farrow), including history carry (shiftin!,
@@ -160,8 +170,8 @@ int32_t mrb_seek(mrb_filter *f, int64_t n0, const void *halo, int64_t ld_halo, i
 /* Live tap update (no reference counterpart -- upstream rebuilds the FIRFilter; SURVEY 8f rank 3, host side).
  * Replaces the taps in place: h has the tap dtype and length given at creation, so taps-per-phase, history
  * length, the carried phase state and the per-channel history are all kept.  Banks are rebuilt as mrb_create
- * builds them (src/Filters.jl:21,36,53,73,106-108,138-139); Farrow needs the new host-fitted poly_coeffs
- * (else NULL).  Synchronises the device. */
+ * builds them (src/Filters.jl:21,36,53,73,106-108,138-139); Farrow: poly_coeffs as in mrb_desc (NULL = the
+ * library refits).  Synchronises the device. */
 int32_t mrb_set_taps(mrb_filter *f, const void *h, int64_t h_len, const double *poly_coeffs);
 
 /* number of CUDA kernels this handle has launched (bench.py's gpu_launches) */
@@ -171,8 +181,9 @@ int32_t mrb_launch_count(const mrb_filter *f, int64_t *n);
  * mean duration per mrb_filt call in milliseconds and the number of calls averaged, and clears the record. */
 int32_t mrb_set_timing(mrb_filter *f, int32_t on);
 int32_t mrb_get_timing(mrb_filter *f, double *mean_ms, int64_t *n_calls);
-/* select the kernel family: 0 = automatic (the tiled kernels, k_stream and k_head_warp where applicable),
- * 1 = k_generic alone (the always-correct path the parity tests use as a second opinion) */
+/* select the kernel family: 0 = automatic (tensor-core and tiled kernels, k_stream and k_head_warp where applicable),
+ * 1 = k_generic alone (the always-correct path the parity tests use as a second opinion),
+ * 2 = automatic without the tensor-core kernels (the CUDA-core fast paths: the other arm of the K5 comparison) */
 int32_t mrb_set_kernel_policy(mrb_filter *f, int32_t policy);
 /* name of the kernel that computed the body of the last mrb_filt on this handle ("generic", "stream", "head",
  * "tiled_c64_t24_r12", "unit_f32_l4_r8", "decim_c64_m8", "table_f32", ...; "none" before the first call) */

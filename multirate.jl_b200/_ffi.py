@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmrb.so")
 SOURCES = ["mrb_api.cu"]
-HEADERS = ["mrb_kernels.cuh", "mrb_tiled.cuh", "mrb_unit.cuh", "mrb_decim.cuh", "mrb_table.cuh", "mrb_seq.h", os.path.join("..", "..", "include", "mrb.h")]
+HEADERS = ["mrb_kernels.cuh", "mrb_tiled.cuh", "mrb_unit.cuh", "mrb_decim.cuh", "mrb_table.cuh", "mrb_mma.cuh", "mrb_seq.h", os.path.join("..", "..", "include", "mrb.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC,-ffp-contract=off"]
@@ -26,7 +26,7 @@ F32, F64, C64, C128 = 0, 1, 2, 3
 
 # every symbol include/mrb.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = ["mrb_create", "mrb_destroy", "mrb_get_info", "mrb_outputlength", "mrb_output_count", "mrb_inputlength",
-           "mrb_nextphase", "mrb_taps2pfb", "mrb_filt", "mrb_filt_host", "mrb_set_host_pipeline", "mrb_advance", "mrb_reset", "mrb_setphase",
+           "mrb_nextphase", "mrb_taps2pfb", "mrb_pfb2pnfb", "mrb_filt", "mrb_filt_host", "mrb_set_host_pipeline", "mrb_advance", "mrb_reset", "mrb_setphase",
            "mrb_get_state", "mrb_set_state", "mrb_get_history", "mrb_set_history", "mrb_tapsforphase", "mrb_get_pfb",
            "mrb_seek", "mrb_get_schedule", "mrb_set_taps", "mrb_launch_count", "mrb_set_timing", "mrb_get_timing", "mrb_set_kernel_policy", "mrb_last_kernel", "mrb_last_error", "mrb_version"]
 
@@ -91,6 +91,7 @@ def lib():
         "mrb_outputlength": (i32, [vp, i64, P(i64)]), "mrb_output_count": (i32, [vp, i64, P(i64)]),
         "mrb_inputlength": (i32, [i64, i64, i64, i64, P(i64)]), "mrb_nextphase": (i32, [i64, i64, i64, P(i64)]),
         "mrb_taps2pfb": (i32, [vp, i64, i32, i64, vp]),
+        "mrb_pfb2pnfb": (i32, [vp, i64, i32, i64, i32, vp]),
         "mrb_filt": (i32, [vp, vp, i64, i64, vp, i64, i64, P(i64), vp]),
         "mrb_filt_host": (i32, [vp, vp, i64, i64, vp, i64, i64, P(i64)]),
         "mrb_set_host_pipeline": (i32, [vp, i32, i32]),

@@ -20,6 +20,7 @@
 #include "mrb_unit.cuh"
 #include "mrb_decim.cuh"
 #include "mrb_table.cuh"
+#include "mrb_mma.cuh"
 
 using namespace mrb;
 
@@ -75,6 +76,7 @@ struct TableCtx {
     bool ready = false;
     void *d_taptab = nullptr;          // farrow: R[kSchedChunk][T]
     TabRows rows;                      // table kernel: tap rows + aligned window starts of one slice
+    MmaRows mrows;                     // tensor-core kernel: tap tiles + group window starts of one slice
 };
 constexpr int kMaxHostStreams = 4;
 
@@ -130,6 +132,7 @@ struct mrb_filter {
     UnitPlan unit;                     // fast path for float32 standard / interpolator (mrb_unit.cuh)
     DecPlan decim;                     // fast path for complex64 decimators (mrb_decim.cuh)
     TabPlan table;                     // fast path for arbitrary / farrow on real samples (mrb_table.cuh)
+    MmaPlan mma;                       // tensor-core path for float32 samples (mrb_mma.cuh)
     int policy = 0;
     int host_block_mib = 0, host_streams_n = 0;   // mrb_set_host_pipeline; 0 = MRB_HOST_BLOCK_MIB / MRB_HOST_STREAMS / default
     int num_sms = 148;
@@ -159,6 +162,7 @@ static void free_device(mrb_filter *f) {
         }
         cudaFree(c.d_taptab); c.d_taptab = nullptr;
         tabrows_release(c.rows);
+        mmarows_release(c.mrows);
         c.ready = false;
     }
     cudaFree(f->d_xs); cudaFree(f->d_ys);
@@ -167,6 +171,7 @@ static void free_device(mrb_filter *f) {
     unit_release(f->unit);
     decim_release(f->decim);
     table_release(f->table);
+    mma_release(f->mma);
     for (auto &p : f->tev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (f->own_stream) cudaStreamDestroy(f->own_stream);
     for (auto &hs : f->host_streams) if (hs) cudaStreamDestroy(hs);
@@ -188,6 +193,61 @@ static cudaError_t upload_real(const std::vector<double> &src, void **dst) {
     cudaError_t e = cudaMalloc(dst, std::max<size_t>(tmp.size(), 1) * sizeof(R));
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(R), cudaMemcpyHostToDevice);
+}
+
+// polyfit(y, order), src/support.jl:85-88: least squares on the Vandermonde matrix A[x, p] = x^p, x = 1..n, p = 0..order,
+// coefficients lowest order first.  THE AGREED RECIPE of this library (include/mrb.h, mrb_pfb2pnfb): Householder QR of A
+// in Float64, no column scaling or pivoting, back substitution -- the textbook meaning of Julia's `A \ y` for a full-rank
+// rectangular A.  cond(A) is ~2.4e6 at order 4 and ~1e8 at order 5 (Nphi = 32): different solvers agree to ~1e-10
+// relative, not to the last bit, which is why every binding takes the coefficients from HERE.
+static void polyfit_qr(const double *y, int n, int order, double *coef) {
+    const int m = order + 1;
+    std::vector<double> A((size_t)n * m), b(y, y + n);
+    for (int i = 0; i < n; ++i) {
+        double p = 1.0;
+        for (int j = 0; j < m; ++j) { A[(size_t)i * m + j] = p; p *= (double)(i + 1); }
+    }
+    for (int k = 0; k < m && k < n; ++k) {
+        double norm = 0.0;
+        for (int i = k; i < n; ++i) norm += A[(size_t)i * m + k] * A[(size_t)i * m + k];
+        norm = std::sqrt(norm);
+        if (norm == 0.0) continue;
+        const double alpha = A[(size_t)k * m + k] > 0.0 ? -norm : norm;
+        std::vector<double> v(n - k);
+        for (int i = k; i < n; ++i) v[i - k] = A[(size_t)i * m + k];
+        v[0] -= alpha;
+        double vv = 0.0;
+        for (double e : v) vv += e * e;
+        if (vv == 0.0) continue;
+        for (int j = k; j < m; ++j) {
+            double dot = 0.0;
+            for (int i = k; i < n; ++i) dot += v[i - k] * A[(size_t)i * m + j];
+            const double s2 = 2.0 * dot / vv;
+            for (int i = k; i < n; ++i) A[(size_t)i * m + j] -= s2 * v[i - k];
+        }
+        double dot = 0.0;
+        for (int i = k; i < n; ++i) dot += v[i - k] * b[i];
+        const double s2 = 2.0 * dot / vv;
+        for (int i = k; i < n; ++i) b[i] -= s2 * v[i - k];
+    }
+    for (int k = m - 1; k >= 0; --k) {
+        double acc = k < n ? b[k] : 0.0;
+        for (int j = k + 1; j < m; ++j) acc -= A[(size_t)k * m + j] * coef[j];
+        const double d = k < n ? A[(size_t)k * m + k] : 0.0;
+        coef[k] = d != 0.0 ? acc / d : 0.0;
+    }
+}
+
+// pfb2pnfb(pfb, order), src/Filters.jl:311-321: one polynomial per tap ROW of the bank, fitted over phi = 1..Nphi and
+// stored as Poly{T}, i.e. rounded to the tap type.  bank is phase-major [Nphi][T]; out is [T][order+1].
+static void fit_pnfb(const std::vector<double> &bank, int64_t Nphi, int64_t T, int order, bool tap_f32, double *out) {
+    std::vector<double> row((size_t)Nphi);
+    for (int64_t i = 0; i < T; ++i) {
+        for (int64_t c = 0; c < Nphi; ++c) row[(size_t)c] = bank[(size_t)(c * T + i)];
+        double *co = out + i * (order + 1);
+        polyfit_qr(row.data(), (int)Nphi, order, co);
+        if (tap_f32) for (int p = 0; p <= order; ++p) co[p] = (double)(float)co[p];
+    }
 }
 
 static void init_state(mrb_filter *f) {
@@ -230,9 +290,13 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
                 dh[i] = f->th == MRB_F32 ? (double)((float)h[i + 1] - (float)h[i]) : h[i + 1] - h[i];
             make_bank(dh, f->Nphi, f->T, f->dbank);
         } else {
-            if (!d->poly_coeffs) return fail(MRB_ERR_BAD_ARGUMENT, "farrow needs host-fitted poly_coeffs");
             f->polyorder = d->poly_order;
-            f->pnfb.assign(d->poly_coeffs, d->poly_coeffs + f->T * (d->poly_order + 1));
+            if (d->poly_coeffs) {
+                f->pnfb.assign(d->poly_coeffs, d->poly_coeffs + f->T * (d->poly_order + 1));
+            } else {                                                   // the library's own fit (mrb_pfb2pnfb)
+                f->pnfb.assign((size_t)(f->T * (d->poly_order + 1)), 0.0);
+                fit_pnfb(f->bank, f->Nphi, f->T, d->poly_order, f->th == MRB_F32, f->pnfb.data());
+            }
         }
     } else {
         // FIRFilter(h, ratio) -- src/Filters.jl:158-180
@@ -287,6 +351,8 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
         if (rc != 0) return fail(MRB_ERR_CUDA, "decim_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
         rc = table_prepare(f->table, kind, f->tx, f->ty, f->T, f->rate, prop);
         if (rc != 0) return fail(MRB_ERR_CUDA, "table_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
+        rc = mma_prepare(f->mma, kind, f->tx, f->ty, f->th, f->T, prop);
+        if (rc != 0) return fail(MRB_ERR_CUDA, "mma_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
         CU(cudaDeviceSynchronize());
     }
     *out = f.release();
@@ -300,7 +366,6 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
 extern "C" int32_t mrb_set_taps(mrb_filter *f, const void *hv, int64_t h_len, const double *poly_coeffs) {
     if (!f || !hv) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
     if (h_len != f->hLen) return fail(MRB_ERR_BAD_ARGUMENT, "mrb_set_taps keeps the tap count (%lld), got %lld", (long long)f->hLen, (long long)h_len);
-    if (f->kind == MRB_FARROW && !poly_coeffs) return fail(MRB_ERR_BAD_ARGUMENT, "farrow needs host-fitted poly_coeffs");
     std::vector<double> h((size_t)h_len);
     for (int64_t i = 0; i < h_len; ++i)
         h[i] = f->th == MRB_F32 ? (double)static_cast<const float *>(hv)[i] : static_cast<const double *>(hv)[i];
@@ -315,7 +380,10 @@ extern "C" int32_t mrb_set_taps(mrb_filter *f, const void *hv, int64_t h_len, co
             dh[i] = f->th == MRB_F32 ? (double)((float)h[i + 1] - (float)h[i]) : h[i + 1] - h[i];
         make_bank(dh, f->Nphi, f->T, f->dbank);
     }
-    if (f->kind == MRB_FARROW) f->pnfb.assign(poly_coeffs, poly_coeffs + f->T * (f->polyorder + 1));
+    if (f->kind == MRB_FARROW) {
+        if (poly_coeffs) f->pnfb.assign(poly_coeffs, poly_coeffs + f->T * (f->polyorder + 1));
+        else fit_pnfb(f->bank, f->Nphi, f->T, f->polyorder, f->th == MRB_F32, f->pnfb.data());
+    }
     if (f->device < 0) return MRB_OK;
 
     DeviceGuard guard(f->device);
@@ -530,6 +598,18 @@ extern "C" int32_t mrb_nextphase(int64_t cur, int64_t L, int64_t M, int64_t *nex
     return MRB_OK;
 }
 
+extern "C" int32_t mrb_pfb2pnfb(const void *h, int64_t h_len, int32_t dtype, int64_t n_phi, int32_t order, double *coeffs) {
+    if (!h || !coeffs || h_len < 1 || n_phi < 1 || order < 0 || (dtype != MRB_F32 && dtype != MRB_F64))
+        return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    std::vector<double> hv((size_t)h_len), bank;
+    for (int64_t i = 0; i < h_len; ++i)
+        hv[(size_t)i] = dtype == MRB_F32 ? (double)static_cast<const float *>(h)[i] : static_cast<const double *>(h)[i];
+    const int64_t T = ceil_div(h_len, n_phi);
+    make_bank(hv, n_phi, T, bank);
+    fit_pnfb(bank, n_phi, T, order, dtype == MRB_F32, coeffs);
+    return MRB_OK;
+}
+
 extern "C" int32_t mrb_taps2pfb(const void *h, int64_t h_len, int32_t dtype, int64_t n_phi, void *pfb) {
     if (!h || !pfb || h_len < 1 || n_phi < 1 || (dtype != MRB_F32 && dtype != MRB_F64))
         return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
@@ -704,7 +784,7 @@ static bool launch_head(const GenParams &P, cudaStream_t st) {
 static const char *dispatch_generic(const mrb_filter *f, const GenParams &P, cudaStream_t st) {
     const int key = f->tx * 4 + f->ty;
     const int sms = f->num_sms;
-    if (f->policy == 0) {
+    if (f->policy != 1) {
         bool done = false;
         switch (key) {
         case MRB_F32 * 4 + MRB_F32: done = launch_head<float, float, 1>(P, st); break;
@@ -797,7 +877,7 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
             P.mode = SEQ_INTEGER; P.L = f->L; P.M = f->M; P.p0 = f->phiIdx - 1; P.d0m1 = f->deficit - 1;
             P.k_base = 0; P.nout = N;
             int64_t k_begin = -1;
-            if (f->policy == 0) {
+            if (f->policy != 1) {
                 k_begin = tiled_try_launch(f->tiled, P, st, &f->last_kernel, &f->launches);
                 if (k_begin == -1) k_begin = unit_try_launch(f->unit, P, st, &f->last_kernel, &f->launches);
                 if (k_begin == -1) k_begin = decim_try_launch(f->decim, P, st, &f->last_kernel, &f->launches);
@@ -833,14 +913,24 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 s.pending = true;
                 P.sn = s.d_n; P.k_base = k0; P.nout = cnt;
                 P.sphi = s.d_phi; P.salpha = s.d_a;
-                if (f->policy == 0) {
+                if (f->policy != 1) {
                     // fast path: per-output tap rows built once for all channels, then one dot product per output
                     int64_t head = 0;                          // outputs of the slice whose window reaches the history
                     while (head < cnt && vn[k0 + head] < f->H) ++head;
+                    int64_t kb = -1;
+                    if (f->mma.ok && f->policy == 0) {         // tensor cores first (float32 samples and taps)
+                        int64_t gs32 = 0;                      // widest spread of window starts inside a group of 32 outputs
+                        for (int64_t g0 = 0; g0 < cnt; g0 += kMmaG)
+                            gs32 = std::max(gs32, vn[k0 + std::min<int64_t>(g0 + kMmaG, cnt) - 1] - vn[k0 + g0]);
+                        kb = mma_try_launch(f->mma, tc.mrows, P, f->kind, f->polyorder + 1, f->th == MRB_F32, f->d_bank, f->d_dbank,
+                                            f->d_pnfb, k0, cnt, head, gs32, st, &f->last_kernel, &f->launches);
+                        if (kb == -2) return fail(MRB_ERR_CUDA, "tensor-core launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    }
                     int64_t gspan = 0;                         // widest spread of window starts inside a group of 8 outputs
-                    for (int64_t g0 = 0; g0 < cnt; g0 += kTabGroup)
-                        gspan = std::max(gspan, vn[k0 + std::min(g0 + kTabGroup, cnt) - 1] - vn[k0 + g0]);
-                    const int64_t kb = table_try_launch(f->table, tc.rows, P, f->kind, f->polyorder + 1, f->th == MRB_F32, f->d_bank,
+                    if (kb == -1)
+                        for (int64_t g0 = 0; g0 < cnt; g0 += kTabGroup)
+                            gspan = std::max(gspan, vn[k0 + std::min(g0 + kTabGroup, cnt) - 1] - vn[k0 + g0]);
+                    if (kb == -1) kb = table_try_launch(f->table, tc.rows, P, f->kind, f->polyorder + 1, f->th == MRB_F32, f->d_bank,
                                                         f->d_dbank, f->d_pnfb, f->rate, k0, cnt, head, gspan, st, &f->last_kernel,
                                                         &f->launches);
                     if (kb == -2) return fail(MRB_ERR_CUDA, "table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1036,7 +1126,7 @@ extern "C" int32_t mrb_launch_count(const mrb_filter *f, int64_t *n) {
 }
 
 extern "C" int32_t mrb_set_kernel_policy(mrb_filter *f, int32_t policy) {
-    if (!f || policy < 0 || policy > 1) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
+    if (!f || policy < 0 || policy > 2) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
     f->policy = policy;
     return MRB_OK;
 }

@@ -1,0 +1,541 @@
+// mrb_mma.cuh -- tensor-core path (tcgen05, 3xTF32) for float32 samples x float32 taps.
+//
+// A polyphase FIR over many channels is a banded product.  For a GROUP of G consecutive outputs k = gG .. gG+G-1
+//     Y[c, k] = sum_j X[c, a_g + j] * W_g[j, k - gG],       j = 0 .. K-1
+// where a_g is the (8-sample aligned) start of the window the group's outputs share and column k of W_g holds the
+// taps of output k (src/Filters.jl:284-298 bank rows; for the arbitrary-rate kinds the per-output row
+// pfb[:,phi]+alpha*dpfb[:,phi] of :681-686 or the Farrow row of :789-791), shifted down by (window start of k) - a_g.
+// With lane = channel this is D[128 channels x G] = A[128 x K] * B[K x G]: a real dense contraction (density T/K,
+// 60-80 % at the BASELINE shapes), which the CUDA cores can only feed through shared-memory tap broadcasts
+// (mrb_table.cuh: LSU bound at 24 % of FP32).  Here it runs on the 5th-generation tensor cores:
+//
+//  * kind::tf32 UMMA, M = 128 (channels), N = G, K = 8 per instruction, accumulators in TENSOR MEMORY;
+//  * float32 accuracy through the 3xTF32 split  x = xh + xl, w = wh + wl,  y ~ xh*wh + xh*wl + xl*wh  (each part exactly
+//    representable in tf32, round-to-nearest splits; the dropped xl*wl term is 2^-22 relative);
+//  * A (the samples) lives in tensor memory as well: a RING OF COLUMNS, lane = channel, column = sample index mod RC.
+//    Converter warps read every TMA box of x once from shared memory, split it and write xh / xl with tcgen05.st --
+//    so a sample is converted once however many groups use it, shared memory holds only the boxes in flight, and the
+//    MMAs read only B from shared memory (TS mode: SS mode would re-read the 128-row A tile for every instruction);
+//  * B (the tap tiles, already split and stored as the K-major SWIZZLE_128B shared-memory image) is built once per
+//    chunk for all channels by a pre-pass (k_mma_tiles) and streamed by bulk copies;
+//  * warp-specialised, no CTA-wide barrier in the loop: x loader, tile loader, MMA issuer (one elected lane),
+//    4 converter warps, 4 epilogue warps (tcgen05.ld -> swizzled staging -> TMA store), all coupled by mbarriers;
+//    tcgen05.commit releases tile slots, ring columns and hands accumulators to the epilogue.
+// Outputs whose window reaches into the history are computed by k_generic, as for every fast path.
+#pragma once
+#include <cstdio>
+
+#include "mrb_tiled.cuh"
+
+namespace mrb {
+
+constexpr int kMmaRows = 128;           // channels per CTA = UMMA M
+constexpr int kMmaBox = 32;             // samples per TMA box row (128 B) = one swizzle atom of K
+constexpr int kMmaBoxBytes = kMmaRows * kMmaBox * 4;     // 16 KB
+constexpr int kMmaNXB = 4;              // x boxes in flight in shared memory
+constexpr int kMmaNAB = 7;              // boxes the tensor-memory rings hold (RC = 224 columns each)
+constexpr int kMmaRC = kMmaNAB * kMmaBox;
+constexpr int kMmaMaxKB = 6;            // K <= 192: the MMAs of a group read at most 7 boxes
+constexpr int kMmaThreads = 352;        // warps 0-3 epilogue, 4-7 converters, 8 x loader, 9 tile loader, 10 MMA issuer
+constexpr int kMmaMaxGT = 512;          // groups per time tile (their window starts are staged in shared memory)
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers (tcgen05)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// the mbarrier is arrived at once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor], kind::tf32
+__device__ __forceinline__ void umma_ts_tf32(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 bytes apart, version 1)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+                 "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
+}
+// round to nearest (ties away) to tf32: the low 13 mantissa bits of the result are zero
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pre-pass: the tap tiles of a schedule slice.  One warp per output row.
+//   group g = k / G holds outputs gG .. gG+G-1; its window starts at gstart[g] = floor8(sn[gG] - H)
+//   tile g = [hi | lo] x [KB atoms][G rows][32 floats], the K-major SWIZZLE_128B image the UMMA B descriptor reads:
+//   element (row r, k index j) at  atom (j>>5) : r*128 + (((j&31)>>2 ^ (r&7)) << 4) + (j&3)*4  bytes
+//   row r, index j = tap (j - d) of output gG+r,  d = (sn[k] - H) - gstart[g]   (zero outside the T taps)
+// `mode`: 0 arbitrary (pfb + alpha*dpfb), 1 farrow (Horner), 2 integer schedule (branch sphi[k] of pfb, no blend)
+// ---------------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+k_mma_tiles(const float *__restrict__ pfb, const float *__restrict__ dpfb, const double *__restrict__ pnfb, int P1, int T, int KB,
+            int mode, int tap_is_f32, const int64_t *__restrict__ sn, const int32_t *__restrict__ sphi,
+            const double *__restrict__ sa, int64_t H, int64_t nout, int64_t nrows, float *__restrict__ tiles,
+            int32_t *__restrict__ gstart) {
+    const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= nrows) return;                                          // nrows = groups * G
+    const int lane = threadIdx.x & 31;
+    const int64_t g = k / G;
+    const int r = (int)(k - g * G);
+    const int64_t xg = sn[g * G] - H;                                // the group's first output exists (g*G < nout)
+    const int64_t al = xg >= 0 ? (xg & ~(int64_t)7) : -(((-xg) + 7) & ~(int64_t)7);
+    if (r == 0 && lane == 0) gstart[g] = (int32_t)al;
+    const bool live = k < nout;
+    const int d = live ? (int)(sn[k] - H - al) : 0;
+    const double ph = live && mode != 2 ? sa[k] : 0.0;               // farrow: phase; arbitrary: alpha
+    const int64_t obase = (live && mode != 1) ? (int64_t)sphi[k] * T : 0;
+    const int64_t tile_floats = (int64_t)2 * KB * G * 32;
+    float *th = tiles + g * tile_floats, *tl = th + (int64_t)KB * G * 32;
+    for (int j = lane; j < KB * 32; j += 32) {
+        const int i = j - d;
+        float v = 0.f;
+        if (live && i >= 0 && i < T) {
+            if (mode == 1) {
+                // currentTaps[i] = polyval(pnfb[i], phase): Horner highest order first in Float64, separately rounded
+                // multiply and add, rounded to the tap type (src/Filters.jl:789-791)
+                const double *c = pnfb + (int64_t)i * P1;
+                double a = c[P1 - 1];
+                for (int p = P1 - 2; p >= 0; --p) a = __dadd_rn(__dmul_rn(a, ph), c[p]);
+                v = (float)a;
+            } else if (mode == 0) {
+                v = (float)((double)pfb[obase + i] + ph * (double)dpfb[obase + i]);   // tapsforphase, :681-686
+            } else {
+                v = pfb[obase + i];
+            }
+        }
+        const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
+        const int off = (j >> 5) * (G * 32) + r * 32 + ((((j & 31) >> 2) ^ (r & 7)) << 2) + (j & 3);
+        th[off] = hi;
+        tl[off] = lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(16) MmaParams {
+    long long g_begin, g_end;  // groups [g_begin, g_end) of the slice
+    long long y0;              // output index of slice output 0 in y
+    int GT;                    // groups per time tile
+    int KB;                    // swizzle atoms (32 samples) per tile row: tile K extent = 32 KB
+    int KS;                    // K-steps (8 samples) actually issued per group (<= 4 KB)
+    int NWB;                   // tile slots in shared memory
+    int tile_bytes;            // 2 * KB * G * 128
+    int pad;
+    long long *prof;           // development aid (MRB_MMA_PROF=1): per CTA 16 counters of cycles spent waiting, see below
+};
+
+template <int G>
+struct MmaCfg {
+    static constexpr int OUT_BYTES = kMmaRows * G * 4;                // staging buffer of one group (G = 32: 128-byte rows)
+    static constexpr int TM_D = 0;                                    // accumulators: 2 x G columns
+    static constexpr int TM_AH = 2 * G;                               // hi ring
+    static constexpr int TM_AL = 2 * G + kMmaRC;                      // lo ring
+    static_assert(2 * G + 2 * kMmaRC <= 512, "tensor memory holds 512 columns");
+    static_assert(G == 32, "the epilogue stages 128-byte rows");
+};
+
+// dynamic shared memory: x ring, tile ring, 2 staging buffers, window starts, 64 mbarrier slots, 1 KiB of alignment slack
+static inline int mma_smem_fixed(int G) { return kMmaNXB * kMmaBoxBytes + 2 * kMmaRows * G * 4 + (kMmaMaxGT + 8) * 4 + 8 * 64 + 1024; }
+
+// mbarrier wait that adds the cycles it spent to `acc` when profiling is on
+__device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bool prof, long long &acc) {
+    if (!prof) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kMmaThreads, 1)
+k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float *__restrict__ tiles,
+          const int32_t *__restrict__ gstart, const __grid_constant__ MmaParams P) {
+    using C = MmaCfg<G>;
+    constexpr int NXB = kMmaNXB, NAB = kMmaNAB;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // dynamic shared memory is only guaranteed 16-byte aligned: the swizzled regions need 1 KiB
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *xring = smem;                                       // NXB boxes [128 ch][32 samples], SWIZZLE_128B
+    unsigned char *wring = xring + NXB * kMmaBoxBytes;                 // NWB tiles
+    unsigned char *oring = wring + P.NWB * P.tile_bytes;               // 2 staging buffers [128 ch][G outputs], SWIZZLE_128B
+    int *gs_raw = reinterpret_cast<int *>(oring + 2 * C::OUT_BYTES);   // window starts of the tile's groups (16-byte granules)
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(gs_raw + kMmaMaxGT + 8);
+    uint32_t *tmem_base_p = reinterpret_cast<uint32_t *>(bars + 40);   // written by tcgen05.alloc
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int ch0 = blockIdx.x * kMmaRows;
+    const long long g0 = P.g_begin + (long long)blockIdx.y * P.GT;     // first group of the tile
+    const int ng = (int)min((long long)P.GT, P.g_end - g0);
+    const long long gal = g0 & ~3ll;                                   // bulk copies start on 16-byte boundaries
+    const int *gs = gs_raw + (int)(g0 - gal);
+
+    const uint32_t bar0 = smem_u32(bars);
+    auto B_XFULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };                 // NXB
+    auto B_XEMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(4 + i); };          // NXB
+    auto B_AFULL = [&](int i) { return bar0 + 8u * (uint32_t)(8 + i); };           // NAB
+    auto B_AEMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(16 + i); };         // NAB
+    auto B_WFULL = [&](int i) { return bar0 + 8u * (uint32_t)(24 + i); };          // NWB <= 4
+    auto B_WEMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(28 + i); };
+    auto B_DFULL = [&](int i) { return bar0 + 8u * (uint32_t)(32 + i); };          // 2
+    auto B_DEMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(34 + i); };
+    const uint32_t B_GS = bar0 + 8u * 36u;
+
+    if (tid == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
+        for (int i = 0; i < NXB; ++i) { mbar_init(B_XFULL(i), 1); mbar_init(B_XEMPTY(i), 128); }
+        for (int i = 0; i < NAB; ++i) { mbar_init(B_AFULL(i), 128); mbar_init(B_AEMPTY(i), 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(B_WFULL(i), 1); mbar_init(B_WEMPTY(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(B_DFULL(i), 1); mbar_init(B_DEMPTY(i), 128); }
+        mbar_init(B_GS, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmy) : "memory");
+        // the window starts of this tile's groups (whole 16-byte granules; the host allocates the slack)
+        const uint32_t bytes = (uint32_t)(((int)(g0 - gal) + ng + 3) / 4 * 16);
+        mbar_expect_tx(B_GS, bytes);
+        bulk_load(smem_u32(gs_raw), gstart + gal, bytes, B_GS);
+    }
+    if (warp == 10) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_base_p)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = *tmem_base_p;
+    const bool prof = P.prof != nullptr;
+    long long *pr = prof ? P.prof + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+    long long c0 = 0, c1 = 0, c2 = 0;                                  // cycles this role spent in its waits
+    const long long t_start = prof ? clock64() : 0;
+
+    mbar_wait(B_GS, 0);                                                // every role needs the window starts
+    const int xbase = gs[0] & ~(kMmaBox - 1);                          // sample index of box 0 of the tile (gstart >= 0 here)
+    const int jlast = (gs[ng - 1] - xbase + P.KS * 8 - 1) / kMmaBox;   // newest box the tile reads
+
+    if (warp == 8) {
+        // ---------------- x loader: TMA boxes into the shared-memory ring
+        if (elect_one()) {
+            for (int j = 0; j <= jlast; ++j) {
+                const int s = j % NXB;
+                if (j >= NXB) mbar_wait_prof(B_XEMPTY(s), (uint32_t)((j / NXB - 1) & 1), prof, c0);
+                mbar_expect_tx(B_XFULL(s), kMmaBoxBytes);
+                tma_load_2d(smem_u32(xring) + (uint32_t)(s * kMmaBoxBytes), &tmx, xbase + j * kMmaBox, ch0, B_XFULL(s));
+            }
+            if (prof) { pr[0] = c0; pr[15] = clock64() - t_start; }
+        }
+    } else if (warp == 9) {
+        // ---------------- tile loader: one bulk copy per group
+        if (elect_one()) {
+            for (int w = 0; w < ng; ++w) {
+                const int s = w % P.NWB;
+                if (w >= P.NWB) mbar_wait_prof(B_WEMPTY(s), (uint32_t)((w / P.NWB - 1) & 1), prof, c0);
+                mbar_expect_tx(B_WFULL(s), (uint32_t)P.tile_bytes);
+                bulk_load(smem_u32(wring) + (uint32_t)(s * P.tile_bytes),
+                          reinterpret_cast<const unsigned char *>(tiles) + (size_t)(g0 + w) * (size_t)P.tile_bytes,
+                          (uint32_t)P.tile_bytes, B_WFULL(s));
+            }
+            if (prof) pr[1] = c0;
+        }
+    } else if (warp == 10) {
+        // ---------------- MMA issuer
+        const uint32_t idesc = umma_idesc_tf32(kMmaRows, G);
+        const uint32_t lo_off = (uint32_t)(P.KB * G * 128) >> 4;       // hi -> lo half of a tile, in descriptor units
+        int boxes_ready = 0, dead = 0;
+        for (int w = 0; w < ng; ++w) {
+            const int a0 = gs[w] - xbase;                              // multiple of 8
+            const int need = (a0 + P.KS * 8 - 1) / kMmaBox;
+            for (; boxes_ready <= need; ++boxes_ready)
+                mbar_wait_prof(B_AFULL(boxes_ready % NAB), (uint32_t)((boxes_ready / NAB) & 1), prof, c0);
+            const int ws = w % P.NWB;
+            mbar_wait_prof(B_WFULL(ws), (uint32_t)((w / P.NWB) & 1), prof, c1);
+            if (w >= 2) mbar_wait_prof(B_DEMPTY(w & 1), (uint32_t)((w / 2 - 1) & 1), prof, c2);
+            tc_fence_after();
+            const uint32_t d = tb + (uint32_t)(C::TM_D + (w & 1) * G);
+            const uint64_t bh0 = umma_desc_sw128(smem_u32(wring) + (uint32_t)(ws * P.tile_bytes));
+            int col = a0 % kMmaRC;
+            if (elect_one()) {
+#pragma unroll 1
+                for (int ks = 0; ks < P.KS; ++ks) {
+                    const uint64_t bh = bh0 + (uint64_t)(((uint32_t)((ks >> 2) * G * 128 + (ks & 3) * 32)) >> 4);
+                    const uint64_t bl = bh + lo_off;
+                    umma_ts_tf32(d, tb + (uint32_t)(C::TM_AH + col), bh, idesc, ks > 0 ? 1u : 0u);
+                    umma_ts_tf32(d, tb + (uint32_t)(C::TM_AH + col), bl, idesc, 1u);
+                    umma_ts_tf32(d, tb + (uint32_t)(C::TM_AL + col), bh, idesc, 1u);
+                    col += 8;
+                    if (col == kMmaRC) col = 0;
+                }
+                tc_commit(B_WEMPTY(ws));                               // the tile slot may be refilled
+                tc_commit(B_DFULL(w & 1));                             // the accumulators are complete
+                // ring boxes no later group reads: everything before the next group's first box
+                const int next_first = w + 1 < ng ? (gs[w + 1] - xbase) / kMmaBox : need + 1;
+                for (int b = dead; b < next_first; ++b) tc_commit(B_AEMPTY(b % NAB));
+            }
+            __syncwarp();
+            {
+                const int next_first = w + 1 < ng ? (gs[w + 1] - xbase) / kMmaBox : need + 1;
+                if (next_first > dead) dead = next_first;
+            }
+        }
+        if (prof && lane == 0) { pr[2] = c0; pr[3] = c1; pr[4] = c2; pr[14] = clock64() - t_start; }
+    } else if (warp >= 4) {
+        // ---------------- converters: thread = channel = tensor-memory lane; box j -> columns (j mod NAB) * 32 of both rings
+        const int q = warp - 4;                                        // lane quadrant (warp index mod 4)
+        const int row = q * 32 + lane;
+        const uint32_t lanebase = tb + ((uint32_t)(q * 32) << 16);
+        const uint32_t rowpart = ((uint32_t)row * 128u) ^ (((uint32_t)row & 7u) << 4);     // SWIZZLE_128B
+        for (int j = 0; j <= jlast; ++j) {
+            const int s = j % NXB, as = j % NAB;
+            mbar_wait_prof(B_XFULL(s), (uint32_t)((j / NXB) & 1), prof, c0);
+            if (j >= NAB) {
+                mbar_wait_prof(B_AEMPTY(as), (uint32_t)((j / NAB - 1) & 1), prof, c1);
+                tc_fence_after();
+            }
+            const uint32_t src = smem_u32(xring) + (uint32_t)(s * kMmaBoxBytes);
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                float x[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t ad = src + (rowpart ^ ((uint32_t)(hlf * 4 + c) << 4));
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(x[4 * c]), "=f"(x[4 * c + 1]), "=f"(x[4 * c + 2]), "=f"(x[4 * c + 3]) : "r"(ad) : "memory");
+                }
+                uint32_t vh[16], vl[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float h = tf32_rna(x[e]);
+                    vh[e] = __float_as_uint(h);
+                    vl[e] = __float_as_uint(tf32_rna(x[e] - h));
+                }
+                tmem_st16(lanebase + (uint32_t)(C::TM_AH + as * kMmaBox + hlf * 16), vh);
+                tmem_st16(lanebase + (uint32_t)(C::TM_AL + as * kMmaBox + hlf * 16), vl);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(B_AFULL(as));
+            mbar_arrive(B_XEMPTY(s));
+        }
+        if (prof && tid == 128) { pr[5] = c0; pr[6] = c1; pr[13] = clock64() - t_start; }
+    } else {
+        // ---------------- epilogue: warp q reads tensor-memory lanes 32q .. 32q+31 (its channels), stages, stores
+        const int row = warp * 32 + lane;
+        const uint32_t lanebase = tb + ((uint32_t)(warp * 32) << 16);
+        const uint32_t rowpart = ((uint32_t)row * 128u) ^ (((uint32_t)row & 7u) << 4);
+        for (int w = 0; w < ng; ++w) {
+            mbar_wait_prof(B_DFULL(w & 1), (uint32_t)((w / 2) & 1), prof, c0);
+            tc_fence_after();
+            uint32_t v[G];
+            tmem_ld16(lanebase + (uint32_t)(C::TM_D + (w & 1) * G), v);
+            tmem_ld16(lanebase + (uint32_t)(C::TM_D + (w & 1) * G + 16), v + 16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(B_DEMPTY(w & 1));
+            // the staging buffer of group w-2 must have been read by its TMA store
+            if (tid == 0) {
+                const long long t0 = prof ? clock64() : 0;
+                tma_wait_read<1>();
+                if (prof) c1 += clock64() - t0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const uint32_t ob = smem_u32(oring) + (uint32_t)((w & 1) * C::OUT_BYTES);
+#pragma unroll
+            for (int c = 0; c < G / 4; ++c) {
+                const uint32_t ad = ob + (rowpart ^ ((uint32_t)c << 4));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "r"(v[4 * c]), "r"(v[4 * c + 1]), "r"(v[4 * c + 2]),
+                             "r"(v[4 * c + 3]) : "memory");
+            }
+            fence_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 0) {
+                tma_store_2d(&tmy, (int)(P.y0 + (g0 + w) * G), ch0, ob);
+                tma_commit();
+            }
+        }
+        if (tid == 0) tma_wait_read<0>();
+        if (prof && tid == 0) { pr[7] = c0; pr[8] = c1; pr[12] = clock64() - t_start; pr[9] = ng; pr[10] = jlast + 1; }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 10) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMmaG = 32;
+
+struct MmaRows {                       // per pipeline stream (TableCtx): the tap tiles and window starts of one slice
+    float *d_tiles = nullptr;
+    int32_t *d_gstart = nullptr;
+    int64_t cap_groups = 0;
+    int64_t tile_bytes = 0;
+};
+
+static inline void mmarows_release(MmaRows &r) {
+    cudaFree(r.d_tiles); cudaFree(r.d_gstart);
+    r = MmaRows{};
+}
+
+struct MmaPlan {
+    bool ok = false;
+    int T = 0;
+    PFN_encodeTiled encode = nullptr;
+    int num_sms = 148;
+    int max_smem = 0;
+};
+
+static inline void mma_release(MmaPlan &p) { p.ok = false; }
+
+// kind/tx/ty are the mrb.h enums (4 arbitrary, 5 farrow ; 0 = float32)
+static inline int32_t mma_prepare(MmaPlan &p, int kind, int tx, int ty, int th, int64_t T, const cudaDeviceProp &prop) {
+    p.ok = false;
+    static const bool off = getenv("MRB_NO_MMA") != nullptr;
+    if (off || !(kind == 4 || kind == 5) || tx != 0 || ty != 0 || th != 0) return 0;
+    if (T + 7 > kMmaMaxKB * 32) return 0;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return (int32_t)(e ? e : cudaErrorUnknown);
+    p.encode = (PFN_encodeTiled)fn;
+    p.num_sms = prop.multiProcessorCount;
+    p.T = (int)T;
+    p.max_smem = (int)prop.sharedMemPerBlockOptin;
+    e = cudaFuncSetAttribute(k_mma_fir<kMmaG>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.max_smem);
+    if (e != cudaSuccess) return (int32_t)e;
+    p.ok = true;
+    return 0;
+}
+
+static inline cudaError_t mma_reserve(MmaRows &r, int64_t groups, int64_t tile_bytes) {
+    if (r.cap_groups >= groups && r.tile_bytes == tile_bytes) return cudaSuccess;
+    mmarows_release(r);
+    cudaError_t e = cudaMalloc(&r.d_tiles, (size_t)groups * (size_t)tile_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&r.d_gstart, (size_t)(groups + 8) * sizeof(int32_t));
+    if (e != cudaSuccess) return e;
+    r.cap_groups = groups; r.tile_bytes = tile_bytes;
+    return cudaSuccess;
+}
+
+// One schedule slice: outputs [0, cnt) (y index y0 + k), the first `head` of which have windows that reach into the
+// history; max_group_span = widest spread of window starts inside a group of kMmaG outputs.  Builds the tap tiles, then
+// launches the main kernel for the groups from the first whole group behind the head.  Returns the first output the
+// kernel covers (the caller computes the outputs before it with the generic kernel), -1 when not covered, -2 on error.
+static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G, int kind, int P1, int tap_is_f32,
+                                     const void *d_pfb, const void *d_dpfb, const double *d_pnfb, int64_t y0, int64_t cnt,
+                                     int64_t head, int64_t max_group_span, cudaStream_t st, const char **name, int64_t *launches) {
+    static const bool trace = getenv("MRB_TRACE") != nullptr;
+#define MRB_MMA_SKIP(why) do { if (trace) fprintf(stderr, "[mrb] tensor-core kernel not used: %s\n", why); return -1; } while (0)
+    if (!p.ok) MRB_MMA_SKIP("configuration not covered");
+    constexpr int GG = kMmaG;
+    if (((uintptr_t)G.x & 15) || ((uintptr_t)G.y & 15) || (G.ldx % 4) || (G.ldy % 4)) MRB_MMA_SKIP("alignment");
+    if (G.n_in >= (1ll << 31) - 4096 || y0 + cnt >= (1ll << 31) - 4096) MRB_MMA_SKIP("size");
+    if (y0 % GG) MRB_MMA_SKIP("slice start");
+    const int64_t kneed = p.T + 7 + max_group_span;                   // samples a group's window spans at worst
+    const int KB = (int)ceil_div(kneed, 32);
+    if (KB > kMmaMaxKB) MRB_MMA_SKIP("window group wider than the tensor-memory ring");
+    const int KS = (int)ceil_div(kneed, 8);
+    const int64_t k_begin = (head + GG - 1) / GG * GG;
+    const int64_t groups = ceil_div(cnt, GG), g_begin = k_begin / GG;
+    if (groups - g_begin < 8) MRB_MMA_SKIP("slice too short");
+    const int tile_bytes = 2 * KB * GG * 128;
+    const int fixed = mma_smem_fixed(GG);
+    const int nwb = std::min(4, (p.max_smem - fixed) / tile_bytes);
+    if (nwb < 2) MRB_MMA_SKIP("shared memory");
+    if (mma_reserve(rw, groups, tile_bytes) != cudaSuccess) return -2;
+
+    {   // pre-pass: one warp per row of every group (rows past the last output are zero)
+        const int64_t nrows = groups * GG;
+        const unsigned gb = (unsigned)ceil_div(nrows, 8);
+        k_mma_tiles<GG><<<gb, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, KB, kind == 5 ? 1 : 0,
+                                            tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt, nrows, rw.d_tiles, rw.d_gstart);
+        ++*launches;
+    }
+    MmaParams P{};
+    static long long *d_prof = nullptr;
+    static const bool want_prof = getenv("MRB_MMA_PROF") != nullptr;
+    if (want_prof && !d_prof) { cudaMalloc(&d_prof, 16 * 8 * 4096); cudaMemset(d_prof, 0, 16 * 8 * 4096); }
+    P.prof = want_prof ? d_prof : nullptr;
+    P.g_begin = g_begin; P.g_end = groups; P.y0 = y0; P.KB = KB; P.KS = KS; P.NWB = nwb; P.tile_bytes = tile_bytes;
+    const int64_t span = groups - g_begin;
+    const int64_t cgroups = ceil_div(G.nch, kMmaRows);
+    // time tiles: one CTA per SM, whole waves where the shape allows, at least 16 groups per tile
+    int64_t tiles = std::max<int64_t>(1, std::min<int64_t>(span / 16, std::max<int64_t>(1, (int64_t)p.num_sms / cgroups)));
+    if (ceil_div(span, tiles) > kMmaMaxGT) tiles = ceil_div(span, kMmaMaxGT);
+    P.GT = (int)ceil_div(span, tiles);
+    tiles = ceil_div(span, P.GT);
+
+    CUtensorMap tmx, tmy;
+    cuuint64_t dims[2] = {(cuuint64_t)G.n_in, (cuuint64_t)G.nch};
+    cuuint64_t strides[1] = {(cuuint64_t)G.ldx * 4};
+    cuuint32_t box[2] = {kMmaBox, kMmaRows};
+    cuuint32_t ones[2] = {1, 1};
+    if (p.encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(G.x), dims, strides, box, ones,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        MRB_MMA_SKIP("x tensor map");
+    cuuint64_t ydims[2] = {(cuuint64_t)(y0 + cnt), (cuuint64_t)G.nch};
+    cuuint64_t ystrides[1] = {(cuuint64_t)G.ldy * 4};
+    cuuint32_t ybox[2] = {GG, kMmaRows};
+    if (p.encode(&tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, G.y, ydims, ystrides, ybox, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        MRB_MMA_SKIP("y tensor map");
+#undef MRB_MMA_SKIP
+    dim3 grid((unsigned)cgroups, (unsigned)tiles);
+    k_mma_fir<GG><<<grid, kMmaThreads, fixed + nwb * tile_bytes, st>>>(tmx, tmy, rw.d_tiles, rw.d_gstart, P);
+    if (cudaPeekAtLastError() != cudaSuccess) return -2;
+    if (want_prof && (int64_t)cgroups * tiles <= 4096) {
+        static int shown = 0;
+        if (shown++ < 3) {
+            std::vector<long long> hp((size_t)cgroups * tiles * 16);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost);
+            double s[16] = {};
+            for (size_t i = 0; i < hp.size(); ++i) s[i % 16] += (double)hp[i] / (double)(cgroups * tiles);
+            fprintf(stderr, "[mrb] mma prof (mean cycles per CTA, %lld CTAs, %.0f groups, %.0f boxes): xload wait-empty %.0f | wload wait-empty %.0f | "
+                            "mma wait a_full %.0f w_full %.0f d_empty %.0f total %.0f | conv wait x_full %.0f a_empty %.0f total %.0f | "
+                            "epi wait d_full %.0f tma-read %.0f total %.0f\n",
+                    (long long)(cgroups * tiles), s[9], s[10], s[0], s[1], s[2], s[3], s[4], s[14], s[5], s[6], s[13], s[7], s[8], s[12]);
+        }
+    }
+    *name = "mma_f32_g32";
+    ++*launches;
+    return k_begin;
+}
+
+}  // namespace mrb

@@ -52,9 +52,18 @@ def polyfit(y, polyorder):
 
 def pfb2pnfb(pfb, polyorder):
     """pfb2pnfb(pfb, order), src/Filters.jl:311-321: one polynomial per tap row, stored as Poly{T}
-    (coefficients rounded to the tap type).  Returned as float64 (tapsPerphi, order+1)."""
+    (coefficients rounded to the tap type).  Returned as float64 (tapsPerphi, order+1).
+    The fit is the library's (mrb_pfb2pnfb: Householder QR in Float64), the one recipe every binding shares --
+    the problem is ill-conditioned enough that numpy's SVD solve and Julia's QR differ in the 10th digit."""
     pfb = np.asarray(pfb)
-    return np.stack([polyfit(pfb[i, :], polyorder).astype(pfb.dtype).astype(np.float64) for i in range(pfb.shape[0])])
+    if pfb.dtype not in (np.float32, np.float64):
+        pfb = pfb.astype(np.float64)
+    T, Nphi = pfb.shape
+    # the bank back to the tap vector it came from (taps2pfb, src/Filters.jl:284-298): h[r*Nphi + c] = pfb[T-1-r, c]
+    h = np.ascontiguousarray(pfb[::-1, :].reshape(-1))
+    out = np.empty((T, int(polyorder) + 1), dtype=np.float64)
+    _ffi.check(_ffi.lib().mrb_pfb2pnfb(h.ctypes.data, len(h), _DT[h.dtype], int(Nphi), int(polyorder), out.ctypes.data))
+    return out
 
 
 def nextphase(currentphase, ratio):
@@ -231,7 +240,7 @@ class FIRFilter:
     state calls only; filt raises)."""
 
     def __init__(self, h, ratio=Fraction(1, 1), Nphi=None, polyorder=None, *, nchannels=None, sample_dtype=None,
-                 device=0):
+                 device=0, pnfb=None):
         h = np.ascontiguousarray(h)
         if h.dtype not in (np.float32, np.float64):
             h = h.astype(np.float64)
@@ -255,7 +264,9 @@ class FIRFilter:
             else:
                 self._kind = _ffi.FARROW
                 self._polyorder = int(polyorder)
-                self._pnfb = np.ascontiguousarray(pfb2pnfb(taps2pfb(h, self._n_phi), self._polyorder))
+                # Farrow coefficients: the library's fit (mrb_pfb2pnfb), or the caller's own as data
+                self._pnfb = (np.ascontiguousarray(pfb2pnfb(taps2pfb(h, self._n_phi), self._polyorder)) if pnfb is None else
+                              np.ascontiguousarray(np.asarray(pnfb, dtype=np.float64).reshape(self._taps_per_phase, self._polyorder + 1)))
         else:
             self._rate = 0.0
             self._ratio = Fraction(ratio)

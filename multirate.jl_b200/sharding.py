@@ -42,7 +42,7 @@ def segment_plan(filt, n_samples: int, world: int, align: int = 1):
     return plan
 
 
-def filt_long_stream(h, ratio, x, rows_target: int = 8192):
+def filt_long_stream(h, ratio, x, rows_target: int = 8192, halo0=None):
     """One very long single-channel stream at multichannel speed, with no copy and no collective (SURVEY 8e,
     BASELINE configs[4] "one 2^31-sample stream split into segments with tap-length halo").
 
@@ -51,6 +51,11 @@ def filt_long_stream(h, ratio, x, rows_target: int = 8192):
     in closed form), its history is simply the H samples that precede it in memory (the halo), and it produces exactly
     seg*L/M outputs, so the output matrix is the output stream, in place.  The tail that does not fill a segment runs
     through a one-channel filter seeked to its position.  x: 1-D CUDA tensor (torch); returns the 1-D output tensor.
+
+    Across GPUs the same call filters ONE RANK'S SEGMENT of the stream: give every rank a segment that starts at a
+    multiple of M (`segment_bounds(..., align=M)`) and pass `halo0` = the H samples that precede it (None for the
+    first segment).  A segment that starts at a multiple of M starts from the constructor state, so its outputs are
+    the stream's outputs [n0*L/M, ...) and no state or sample crosses between GPUs at run time.
     """
     import math
     from fractions import Fraction
@@ -85,6 +90,8 @@ def filt_long_stream(h, ratio, x, rows_target: int = 8192):
         if H:
             idx = (torch.arange(1, rows, device=x.device) * seg).unsqueeze(1) + torch.arange(-H, 0, device=x.device)
             halo[1:, :H] = x[idx]
+            if halo0 is not None:
+                halo[0, :H] = halo0[-H:]
         k0 = C.c_int64()
         _ffi.check(lib.mrb_seek(f._handle, 0, halo.data_ptr() if H else None, max(H, 1), C.byref(k0), stream))
         f.filt_(y[:rows * seg_out].view(rows, seg_out), body)
@@ -92,7 +99,8 @@ def filt_long_stream(h, ratio, x, rows_target: int = 8192):
     if done_in < n:
         g = FIRFilter(h, ratio, nchannels=1, sample_dtype=tx, device=x.device.index or 0)
         k0 = C.c_int64()
-        halo = x[done_in - H:done_in].contiguous() if (done_in and H) else None
+        halo = x[done_in - H:done_in].contiguous() if (done_in and H) else (
+            halo0[-H:].contiguous() if (halo0 is not None and H) else None)
         _ffi.check(lib.mrb_seek(g._handle, done_in, halo.data_ptr() if halo is not None else None, H, C.byref(k0), stream))
         assert k0.value == done_out
         g.filt_(y[done_out:], x[done_in:])

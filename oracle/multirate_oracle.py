@@ -83,6 +83,20 @@ def polyfit(y, polyorder):
     return coef
 
 
+# The Farrow coefficients are an INPUT of the filtering path (fitted once, at construction).  The least-squares problem
+# is ill-conditioned (cond ~2.4e6 at order 4), so two correct solvers differ around the 10th digit -- more than the
+# Float64 filtering tolerance (1e-12).  Filtering parity therefore takes the coefficients AS DATA: a test may install
+# the fit it wants both sides to use (tests/conftest.py installs the library's mrb_pfb2pnfb); the solve below stays the
+# oracle's own, independent one (numpy SVD) and tests/test_farrow_fit.py compares the two.
+_PNFB_PROVIDER = None
+
+
+def set_pnfb_provider(fn):
+    """fn(pfb, polyorder) -> (T, order+1) float64 coefficients, or None to restore the oracle's own fit."""
+    global _PNFB_PROVIDER
+    _PNFB_PROVIDER = fn
+
+
 def pfb2pnfb(pfb, polyorder):
     """src/Filters.jl:311-321: one polynomial per tap ROW of the bank, fitted over
     phi = 1..Nphi.  Stored as Poly{T} (src/Filters.jl:313), i.e. coefficients are
@@ -196,11 +210,16 @@ class FIRArbitrary:
 
 
 class FIRFarrow:
-    def __init__(self, h, rate, Nphi, polyorder):
+    def __init__(self, h, rate, Nphi, polyorder, pnfb=None):
         h = np.asarray(h)
         self.rate = float(rate)
         self.pfb = taps2pfb(h, Nphi)                    # :138
-        self.pnfb = pfb2pnfb(self.pfb, polyorder)       # :139
+        if pnfb is not None:                            # coefficients as data
+            self.pnfb = np.asarray(pnfb, dtype=np.float64).reshape(self.pfb.shape[0], polyorder + 1)
+        elif _PNFB_PROVIDER is not None:
+            self.pnfb = np.asarray(_PNFB_PROVIDER(self.pfb, polyorder), dtype=np.float64)
+        else:
+            self.pnfb = pfb2pnfb(self.pfb, polyorder)   # :139
         self.polyorder = polyorder
         self.Nphi = Nphi
         self.tapsPerphi = self.pfb.shape[0]
@@ -230,7 +249,7 @@ class FIRFilter:
     FIRFilter per vector; channels never interact).  The sample dtype is fixed by
     the first `filt` call (src/Filters.jl:452: history is converted to Vector{Tx})."""
 
-    def __init__(self, h, ratio=Fraction(1, 1), Nphi=None, polyorder=None):
+    def __init__(self, h, ratio=Fraction(1, 1), Nphi=None, polyorder=None, pnfb=None):
         h = np.asarray(h)
         assert h.dtype in (np.float32, np.float64)
         if isinstance(ratio, float):
@@ -239,7 +258,7 @@ class FIRFilter:
             if polyorder is None:
                 self.kernel = FIRArbitrary(h, ratio, 32 if Nphi is None else Nphi)   # :183-189
             else:
-                self.kernel = FIRFarrow(h, ratio, Nphi, polyorder)       # :192-198
+                self.kernel = FIRFarrow(h, ratio, Nphi, polyorder, pnfb)  # :192-198
             self.historyLen = self.kernel.tapsPerphi - 1
         else:
             ratio = Fraction(ratio)

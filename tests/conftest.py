@@ -10,6 +10,19 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 
+def _install_shared_farrow_fit():
+    """The Farrow coefficients are an input of the filtering path and their least-squares fit is solver dependent at
+    ~1e-10 (cond ~2.4e6): filtering parity uses ONE set of coefficients on both sides -- the library's agreed recipe,
+    mrb_pfb2pnfb (host only, no GPU needed).  tests/test_farrow_fit.py removes the hook and pins that recipe against
+    the oracle's own independent solve."""
+    import multirate_b200 as mr
+    import multirate_oracle as mo
+    mo.set_pnfb_provider(lambda pfb, order: mr.pfb2pnfb(pfb, order))
+
+
+_install_shared_farrow_fit()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 

@@ -53,5 +53,8 @@ for name, ratio, nphi, po in cases:
                 out[key + ".y%d" % i] = y
             out[key + ".state"] = np.array([f.state().get("phiIdx", 1), f.state().get("inputDeficit", 1)], dtype=np.int64)
             out[key + ".fstate"] = np.array([f.state().get("acc", 1.0), f.state().get("alpha", 0.0)], dtype=np.float64)
+            if name == "farrow":
+                # the Farrow coefficients are an input of the path: frozen with the vectors (the fit is solver dependent)
+                out[key + ".pnfb"] = np.asarray(f.kernel.pnfb, dtype=np.float64)
 np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **out)
 print("wrote", len(out), "arrays")
