@@ -503,7 +503,7 @@ def measure_stream(ctx, log2n=31):
     rank filters its segment at multichannel speed (filt_long_stream: the segment viewed in place as a matrix of
     sub-segments).  Device-timed per rank, max over ranks."""
     torch, mr = ctx.torch, ctx.mr
-    from multirate_b200 import sharding
+    sharding = mr                        # segment_bounds / segment_plan / filt_long_stream are package exports
     L, M = 147, 160
     h = design_taps(3528, 0.5 / 147, 7.8562, 1.0)
     n_total = 1 << log2n

@@ -772,10 +772,11 @@ static bool launch_stream(const GenParams &P, int num_sms, int device, cudaStrea
 // k_head_warp: short launches (chunk heads) of integer schedules with long windows
 template <typename RX, typename R, int NC>
 static bool launch_head(const GenParams &P, cudaStream_t st) {
-    if (P.mode != SEQ_INTEGER || P.nout > 256 || P.T < 64 || P.nout * P.nch >= (1ll << 26)) return false;
+    if (P.nout > 256 || P.T < 64 || P.nout * P.nch >= (1ll << 26)) return false;
     // 32x the warps of k_generic: pays when a thread-per-output warp would read M-strided windows (decimating ratios)
-    // or when there are too few outputs to fill the machine with threads (measured: standard-128 x 4096 channels loses)
-    if (P.M < 4 * P.L && P.nout * P.nch >= 8192) return false;
+    // or when there are too few outputs to fill the machine with threads (measured: standard-128 x 4096 channels loses).
+    // Arbitrary-rate heads (two dot products per output, 23 us for 96 outputs x 1024 channels on k_generic) always pay.
+    if (P.mode == SEQ_INTEGER && P.M < 4 * P.L && P.nout * P.nch >= 8192) return false;
     k_head_warp<RX, R, NC><<<(unsigned)ceil_div(P.nout * P.nch * 32, 256), 256, 0, st>>>(P);
     return true;
 }

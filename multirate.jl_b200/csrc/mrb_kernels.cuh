@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) k_generic(const GenParams P) {
     }
 }
 
-// Chunk heads of long filters (integer schedules): the few outputs whose window reaches the history, for every channel.
+// Chunk heads of long filters (every schedule kind): the few outputs whose window reaches the history, for every channel.
 // With one thread per output a warp's loads are T-strided and each lane walks its whole window alone (decimator 1//8 x
 // 256 taps, 1024 channels: 31 us for 40 outputs per channel, 14 % of the step).  Here a WARP computes one output of one
 // channel: lane i takes taps i, i+32, ... (consecutive lanes read consecutive samples and taps), then a shuffle tree.
@@ -168,16 +168,32 @@ __global__ void __launch_bounds__(256) k_head_warp(const GenParams P) {
     if (w >= P.nout * P.nch) return;
     const int64_t c = w / P.nout, kl = w - c * P.nout;
     const int64_t k = P.k_base + kl;
-    const int64_t t = P.p0 + k * P.M;
-    const int64_t tq = t / P.L, tr = t - tq * P.L;
-    const int64_t n = P.d0m1 + tq, H = P.H;
+    const int64_t H = P.H;
     const int T = (int)P.T;
-    const R *__restrict__ taps = static_cast<const R *>(P.bank) + tr * P.T;
+    int64_t n;
+    const R *__restrict__ taps;
+    const R *__restrict__ dtaps = nullptr;
+    double alpha = 0.0;
+    if (P.mode == SEQ_INTEGER) {
+        const int64_t t = P.p0 + k * P.M;
+        const int64_t tq = t / P.L, tr = t - tq * P.L;
+        n = P.d0m1 + tq;
+        taps = static_cast<const R *>(P.bank) + tr * P.T;
+    } else if (P.mode == SEQ_ARBITRARY) {                                        // as k_generic: two dots, Float64 blend (:723-730)
+        n = P.sn[kl];
+        const int64_t phi = P.sphi[kl];
+        taps = static_cast<const R *>(P.bank) + phi * P.T;
+        dtaps = static_cast<const R *>(P.dbank) + phi * P.T;
+        alpha = P.salpha[kl];
+    } else {
+        n = P.sn[kl];
+        taps = static_cast<const R *>(P.taptab) + kl * P.T;
+    }
     const RX *__restrict__ hc = static_cast<const RX *>(P.hist) + c * H * NC;
     const RX *__restrict__ xw = static_cast<const RX *>(P.x) + (c * P.ldx + (n - H)) * NC;
-    R acc[NC];
+    R acc[NC], dacc[NC];
 #pragma unroll
-    for (int q = 0; q < NC; ++q) acc[q] = R(0);
+    for (int q = 0; q < NC; ++q) acc[q] = dacc[q] = R(0);
 #pragma unroll 4
     for (int i = lane; i < T; i += 32) {
         RX s[NC];
@@ -186,11 +202,23 @@ __global__ void __launch_bounds__(256) k_head_warp(const GenParams P) {
         const R tv = __ldg(taps + i);
 #pragma unroll
         for (int q = 0; q < NC; ++q) acc[q] = fma(tv, (R)s[q], acc[q]);
+        if (dtaps) {
+            const R dv = __ldg(dtaps + i);
+#pragma unroll
+            for (int q = 0; q < NC; ++q) dacc[q] = fma(dv, (R)s[q], dacc[q]);
+        }
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1)
 #pragma unroll
-        for (int q = 0; q < NC; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        for (int q = 0; q < NC; ++q) {
+            acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+            dacc[q] += __shfl_xor_sync(0xffffffffu, dacc[q], o);
+        }
+    if (dtaps) {
+#pragma unroll
+        for (int q = 0; q < NC; ++q) acc[q] = (R)((double)acc[q] + (double)dacc[q] * alpha);
+    }
     if (lane == 0) st_sample<R, NC>(static_cast<R *>(P.y) + c * P.ldy * NC, k, acc);
 }
 

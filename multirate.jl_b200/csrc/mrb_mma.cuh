@@ -286,17 +286,21 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
             tc_fence_after();
             const uint32_t d = tb + (uint32_t)(C::TM_D + (w & 1) * G);
             const uint64_t bh0 = umma_desc_sw128(smem_u32(wring) + (uint32_t)(ws * P.tile_bytes));
-            int col = a0 % kMmaRC;
+            const int col0 = a0 % kMmaRC;
             if (elect_one()) {
-#pragma unroll 1
-                for (int ks = 0; ks < P.KS; ++ks) {
+                // Fully unrolled: every K-step's addresses are (group base) + (compile-time constant), so the uniform
+                // datapath sees short independent chains instead of one loop-carried one (a rolled loop issued an MMA
+                // only every ~53 cycles; the tensor pipe takes one N = 32 MMA every 16).
+#pragma unroll
+                for (int ks = 0; ks < 4 * kMmaMaxKB; ++ks) {
+                    if (ks >= P.KS) break;
+                    int col = col0 + 8 * ks;                             // 8 ks < RC: one conditional subtraction wraps the ring
+                    col -= col >= kMmaRC ? kMmaRC : 0;
                     const uint64_t bh = bh0 + (uint64_t)(((uint32_t)((ks >> 2) * G * 128 + (ks & 3) * 32)) >> 4);
                     const uint64_t bl = bh + lo_off;
                     umma_ts_tf32(d, tb + (uint32_t)(C::TM_AH + col), bh, idesc, ks > 0 ? 1u : 0u);
                     umma_ts_tf32(d, tb + (uint32_t)(C::TM_AH + col), bl, idesc, 1u);
                     umma_ts_tf32(d, tb + (uint32_t)(C::TM_AL + col), bh, idesc, 1u);
-                    col += 8;
-                    if (col == kMmaRC) col = 0;
                 }
                 tc_commit(B_WEMPTY(ws));                               // the tile slot may be refilled
                 tc_commit(B_DFULL(w & 1));                             // the accumulators are complete
