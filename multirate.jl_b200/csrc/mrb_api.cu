@@ -59,12 +59,49 @@ static int promote(int th, int tx) {
 // ------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------
-struct SchedSlot {            // pinned host staging + device copy of one table-schedule sub-chunk
-    int64_t *h_n = nullptr, *d_n = nullptr;
-    int32_t *h_phi = nullptr, *d_phi = nullptr;
-    double *h_a = nullptr, *d_a = nullptr;
+struct SchedSlot {            // device copy of one table-schedule sub-chunk
+    int64_t *d_n = nullptr;
+    int32_t *d_phi = nullptr;
+    double *d_a = nullptr;
+};
+
+// Host storage of one replayed schedule: (n, phi, alpha | phase) per output.  PINNED on device-bound handles, so the
+// slices are uploaded straight from it (no staging copy on the host: the arbitrary-rate path at BASELINE configs[3] is
+// bound by host time per chunk, not by the kernels).  Two stores alternate between calls; `ev` marks the last upload
+// that still reads a store, and is waited for before the store is overwritten.
+struct SchedStore {
+    int64_t *n = nullptr;
+    int32_t *phi = nullptr;
+    double *a = nullptr;
+    size_t cap = 0, size = 0;
+    bool pinned = false;
     cudaEvent_t ev = nullptr;
     bool pending = false;
+
+    void release() {
+        if (pinned) { cudaFreeHost(n); cudaFreeHost(phi); cudaFreeHost(a); }
+        else { free(n); free(phi); free(a); }
+        n = nullptr; phi = nullptr; a = nullptr; cap = size = 0;
+        if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+        pending = false;
+    }
+    // room for `want` entries, contents kept; false when out of memory
+    bool reserve(size_t want, bool pin) {
+        if (want <= cap) return true;
+        const size_t ncap = want + want / 8 + 64;
+        int64_t *nn = nullptr; int32_t *np = nullptr; double *na = nullptr;
+        if (pin) {
+            if (cudaMallocHost(&nn, ncap * sizeof(int64_t)) != cudaSuccess || cudaMallocHost(&np, ncap * sizeof(int32_t)) != cudaSuccess ||
+                cudaMallocHost(&na, ncap * sizeof(double)) != cudaSuccess) { cudaFreeHost(nn); cudaFreeHost(np); cudaFreeHost(na); cudaGetLastError(); return false; }
+        } else {
+            nn = (int64_t *)malloc(ncap * sizeof(int64_t)); np = (int32_t *)malloc(ncap * sizeof(int32_t)); na = (double *)malloc(ncap * sizeof(double));
+            if (!nn || !np || !na) { free(nn); free(np); free(na); return false; }
+        }
+        if (size) { memcpy(nn, n, size * sizeof(int64_t)); memcpy(np, phi, size * sizeof(int32_t)); memcpy(na, a, size * sizeof(double)); }
+        if (pinned) { cudaFreeHost(n); cudaFreeHost(phi); cudaFreeHost(a); } else { free(n); free(phi); free(a); }
+        n = nn; phi = np; a = na; cap = ncap; pinned = pin;
+        return true;
+    }
 };
 
 // Everything run_channels WRITES on the device for the arbitrary-rate kinds: the uploaded schedule slices, the Farrow tap
@@ -124,7 +161,8 @@ struct mrb_filter {
     // table kinds: the schedule of the call in flight.  The exact replay costs ~0.3 ms per 60 K outputs, and a caller
     // typically asks for the count (to size its buffer) right before it filters: the last replay is cached, keyed by
     // the state it started from and the input length.
-    std::vector<int64_t> vn; std::vector<int32_t> vphi; std::vector<double> va;
+    SchedStore sched[2];
+    int sched_cur = 0;
     bool sched_valid = false;
     mrb_state sched_from{}, sched_end{};
     int64_t sched_n_in = -1, sched_count = 0;
@@ -149,15 +187,14 @@ struct mrb_filter {
 static const int64_t kSchedChunk = 1 << 16;   // outputs per table-schedule sub-chunk
 
 static void free_device(mrb_filter *f) {
-    if (f->device < 0) return;
+    if (f->device < 0) { for (auto &st : f->sched) st.release(); return; }
     DeviceGuard guard(f->device);
+    for (auto &st : f->sched) st.release();
     cudaFree(f->d_bank); cudaFree(f->d_dbank); cudaFree(f->d_pnfb);
     cudaFree(f->d_hist[0]); cudaFree(f->d_hist[1]);
     for (auto &c : f->tctx) {
         for (auto &s : c.slot) {
-            cudaFreeHost(s.h_n); cudaFreeHost(s.h_phi); cudaFreeHost(s.h_a);
             cudaFree(s.d_n); cudaFree(s.d_phi); cudaFree(s.d_a);
-            if (s.ev) cudaEventDestroy(s.ev);
             s = SchedSlot{};
         }
         cudaFree(c.d_taptab); c.d_taptab = nullptr;
@@ -443,67 +480,59 @@ extern "C" int32_t mrb_outputlength(const mrb_filter *f, int64_t n_in, int64_t *
     return MRB_OK;
 }
 
-// Exact replay for the table kinds.  Fills (n 0-based, phi 0-based / phase, alpha) when the vectors are given.
-static int64_t replay_table(const mrb_filter *f, int64_t n_in, mrb_state *end, std::vector<int64_t> *vn,
-                            std::vector<int32_t> *vphi, std::vector<double> *va) {
+// Exact replay for the table kinds.  Fills the store (n 0-based, phi 0-based, alpha | Float64 phase) when one is given.
+// Returns the output count, or -1 when the store could not grow.
+static int64_t replay_table(const mrb_filter *f, int64_t n_in, mrb_state *end, SchedStore *st) {
     mrb_state s{f->phiIdx, f->deficit, f->xIdx, f->acc, f->alpha};
     int64_t count = 0;
+    if (st) st->size = 0;
     if (n_in < s.input_deficit) {                                       // :705-709, :805-809
         s.input_deficit -= n_in;
-        if (vn) vn->clear();
-        if (va) va->clear();
-        if (vphi) vphi->clear();
     } else {
         ArbState a{s.phi_accumulator, s.input_deficit};                 // xIdx = inputDeficit, :715,:812
         const bool arb = f->kind == MRB_ARBITRARY;
-        if (vn) {
-            // schedule wanted: write through raw pointers into storage sized for the bound of outputlength (:375-381)
-            // plus slack, grown if the loop decides otherwise (push_back and its capacity checks cost as much as the
-            // recurrence itself)
+        const ArbStepper stepper(f->delta, f->Nphi);
+        if (st) {
+            // schedule wanted: written through raw pointers into storage sized for the bound of outputlength (:375-381)
+            // plus slack, grown if the loop decides otherwise
+            const bool pin = f->device >= 0;
             size_t cap = (size_t)((double)(n_in - s.input_deficit + 1) * f->rate) + 16;
-            vn->resize(cap); if (va) va->resize(cap); if (vphi && arb) vphi->resize(cap);
-            int64_t *pn = vn->data(); double *pa = va ? va->data() : nullptr; int32_t *pp = (vphi && arb) ? vphi->data() : nullptr;
+            if (!st->reserve(cap, pin)) return -1;
+            cap = st->cap;
+            int64_t *pn = st->n; double *pa = st->a; int32_t *pp = st->phi;
             size_t c = 0;
             const int64_t phi0 = s.phi_idx;
             const double alpha0 = s.alpha;
             while (a.xIdx <= n_in) {
                 if (c == cap) {
-                    cap += cap / 2 + 16;
-                    vn->resize(cap); pn = vn->data();
-                    if (pa) { va->resize(cap); pa = va->data(); }
-                    if (pp) { vphi->resize(cap); pp = vphi->data(); }
+                    st->size = c;
+                    if (!st->reserve(cap + cap / 2 + 16, pin)) return -1;
+                    cap = st->cap; pn = st->n; pa = st->a; pp = st->phi;
                 }
                 pn[c] = a.xIdx - 1;
-                if (pa) pa[c] = a.acc;       // farrow: the Float64 phiIdx the taps are evaluated at; arbitrary: split below
+                pa[c] = a.acc;               // farrow: the Float64 phiIdx the taps are evaluated at; arbitrary: split below
                 ++c;
-                arb_update(a, f->delta, f->Nphi);
+                stepper.step(a);
             }
             if (arb) {
                 // branch and alpha of every output from the accumulator it started with (:671-672) -- outside the
                 // sequential loop, where the conversion vectorises.  Output 0 keeps the carried pair: setphase may
                 // have clamped it.
-                if (c > 0) {
-                    if (pp) pp[0] = (int32_t)(phi0 - 1);
-                    if (pa) pa[0] = alpha0;
-                }
-                if (pa && pp) {
-                    for (size_t i = 1; i < c; ++i) {
-                        const int32_t ph = (int32_t)pa[i];              // floor of a value in [1, Nphi+1)
-                        pp[i] = ph - 1;
-                        pa[i] -= (double)ph;
-                    }
-                } else if (pa) {
-                    for (size_t i = 1; i < c; ++i) pa[i] -= (double)(int32_t)pa[i];
+                if (c > 0) { pp[0] = (int32_t)(phi0 - 1); pa[0] = alpha0; }
+                for (size_t i = 1; i < c; ++i) {
+                    const int32_t ph = (int32_t)pa[i];                  // floor of a value in [1, Nphi+1)
+                    pp[i] = ph - 1;
+                    pa[i] -= (double)ph;
                 }
                 s.phi_idx = (int64_t)a.acc;
                 s.alpha = a.acc - (double)s.phi_idx;
             }
-            vn->resize(c); if (pa) va->resize(c); if (pp) vphi->resize(c);
+            st->size = c;
             count = (int64_t)c;
         } else {
             while (a.xIdx <= n_in) {
                 ++count;
-                arb_update(a, f->delta, f->Nphi);
+                stepper.step(a);
             }
             if (arb && count > 0) {
                 s.phi_idx = (int64_t)a.acc;
@@ -522,8 +551,16 @@ static int64_t replay_table(const mrb_filter *f, int64_t n_in, mrb_state *end, s
 static int64_t replay_cached(mrb_filter *f, int64_t n_in, mrb_state *end) {
     const mrb_state from{f->phiIdx, f->deficit, f->xIdx, f->acc, f->alpha};
     if (!(f->sched_valid && f->sched_n_in == n_in && memcmp(&from, &f->sched_from, sizeof from) == 0)) {
-        // (the vectors keep their size from the previous call: growing them by a few elements initialises only those)
-        f->sched_count = replay_table(f, n_in, &f->sched_end, &f->vn, f->kind == MRB_ARBITRARY ? &f->vphi : nullptr, &f->va);
+        f->sched_cur ^= 1;                                          // the other store: uploads of the last call may still read this one
+        SchedStore &st = f->sched[f->sched_cur];
+        if (st.pending) {
+            DeviceGuard guard(f->device);
+            cudaEventSynchronize(st.ev);
+            st.pending = false;
+        }
+        f->sched_valid = false;
+        f->sched_count = replay_table(f, n_in, &f->sched_end, &st);
+        if (f->sched_count < 0) { f->sched_count = 0; st.size = 0; return -1; }
         f->sched_from = from; f->sched_n_in = n_in; f->sched_valid = true;
     }
     if (end) *end = f->sched_end;
@@ -542,6 +579,7 @@ static int64_t count_outputs(const mrb_filter *f, int64_t n_in, mrb_state *end) 
 extern "C" int32_t mrb_output_count(const mrb_filter *f, int64_t n_in, int64_t *n_out) {
     if (!f || !n_out || n_in < 0) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
     *n_out = count_outputs(f, n_in, nullptr);
+    if (*n_out < 0) return fail(MRB_ERR_CUDA, "out of memory for the schedule");
     return MRB_OK;
 }
 
@@ -556,12 +594,14 @@ extern "C" int32_t mrb_get_schedule(mrb_filter *f, int64_t n_in, int64_t *n_idx,
     if (!f || n_in < 0) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
     if (is_table_kind(f)) {
         const int64_t N = replay_cached(f, n_in, nullptr);
+        if (N < 0) return fail(MRB_ERR_CUDA, "out of memory for the schedule");
         if (N == 0) return MRB_OK;
-        if (n_idx) memcpy(n_idx, f->vn.data(), (size_t)N * sizeof(int64_t));
-        if (frac) memcpy(frac, f->va.data(), (size_t)N * sizeof(double));
+        const SchedStore &st = f->sched[f->sched_cur];
+        if (n_idx) memcpy(n_idx, st.n, (size_t)N * sizeof(int64_t));
+        if (frac) memcpy(frac, st.a, (size_t)N * sizeof(double));
         if (branch) {
-            if (f->kind == MRB_ARBITRARY) memcpy(branch, f->vphi.data(), (size_t)N * sizeof(int32_t));
-            else for (int64_t k = 0; k < N; ++k) branch[k] = (int32_t)f->va[k] - 1;
+            if (f->kind == MRB_ARBITRARY) memcpy(branch, st.phi, (size_t)N * sizeof(int32_t));
+            else for (int64_t k = 0; k < N; ++k) branch[k] = (int32_t)st.a[k] - 1;
         }
         return MRB_OK;
     }
@@ -580,6 +620,7 @@ extern "C" int32_t mrb_advance(mrb_filter *f, int64_t n_in, int64_t *n_out) {
     if (!f || n_in < 0) return fail(MRB_ERR_BAD_ARGUMENT, "bad argument");
     mrb_state e;
     const int64_t N = count_outputs(f, n_in, &e);
+    if (N < 0) return fail(MRB_ERR_CUDA, "out of memory for the schedule");
     commit_state(f, e);
     if (n_out) *n_out = N;
     return MRB_OK;
@@ -832,13 +873,9 @@ static void launch_history(const mrb_filter *f, const void *x, int64_t ldx, int6
 static int32_t ensure_sched(mrb_filter *f, TableCtx &c) {
     if (c.ready) return MRB_OK;
     for (auto &s : c.slot) {
-        CU(cudaMallocHost(&s.h_n, kSchedChunk * sizeof(int64_t)));
-        CU(cudaMallocHost(&s.h_phi, kSchedChunk * sizeof(int32_t)));
-        CU(cudaMallocHost(&s.h_a, kSchedChunk * sizeof(double)));
         CU(cudaMalloc(&s.d_n, kSchedChunk * sizeof(int64_t)));
         CU(cudaMalloc(&s.d_phi, kSchedChunk * sizeof(int32_t)));
         CU(cudaMalloc(&s.d_a, kSchedChunk * sizeof(double)));
-        CU(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
     }
     if (f->kind == MRB_FARROW)
         CU(cudaMalloc(&c.d_taptab, (size_t)kSchedChunk * f->T * (is_double(f->ty) ? 8 : 4)));
@@ -895,23 +932,20 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
             int32_t rc = ensure_sched(f, tc);
             if (rc) return rc;
             // the exact host replay (data independent) was done by check_filt_args; uploaded in bounded sub-chunks
-            const std::vector<int64_t> &vn = f->vn; const std::vector<int32_t> &vphi = f->vphi; const std::vector<double> &va = f->va;
-            if ((int64_t)vn.size() != N) return fail(MRB_ERR_BAD_ARGUMENT, "internal: schedule not prepared");
+            SchedStore &store = f->sched[f->sched_cur];
+            const int64_t *vn = store.n; const int32_t *vphi = store.phi; const double *va = store.a;
+            if ((int64_t)store.size != N || !f->sched_valid) return fail(MRB_ERR_BAD_ARGUMENT, "internal: schedule not prepared");
+            if (!store.ev) CU(cudaEventCreateWithFlags(&store.ev, cudaEventDisableTiming));
             int si = 0;
             for (int64_t k0 = 0; k0 < N; k0 += kSchedChunk, si ^= 1) {
                 const int64_t cnt = std::min(kSchedChunk, N - k0);
                 SchedSlot &s = tc.slot[si];
-                if (s.pending) { CU(cudaEventSynchronize(s.ev)); s.pending = false; }
-                memcpy(s.h_n, vn.data() + k0, cnt * sizeof(int64_t));
-                memcpy(s.h_a, va.data() + k0, cnt * sizeof(double));
-                CU(cudaMemcpyAsync(s.d_n, s.h_n, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-                CU(cudaMemcpyAsync(s.d_a, s.h_a, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
-                if (f->kind == MRB_ARBITRARY) {
-                    memcpy(s.h_phi, vphi.data() + k0, cnt * sizeof(int32_t));
-                    CU(cudaMemcpyAsync(s.d_phi, s.h_phi, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-                }
-                CU(cudaEventRecord(s.ev, st));
-                s.pending = true;
+                // uploaded straight from the pinned store (stream order keeps a slot's previous readers ahead of this write)
+                CU(cudaMemcpyAsync(s.d_n, vn + k0, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(s.d_a, va + k0, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+                if (f->kind == MRB_ARBITRARY)
+                    CU(cudaMemcpyAsync(s.d_phi, vphi + k0, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                if (k0 + cnt >= N) { CU(cudaEventRecord(store.ev, st)); store.pending = true; }   // the store is free again after this
                 P.sn = s.d_n; P.k_base = k0; P.nout = cnt;
                 P.sphi = s.d_phi; P.salpha = s.d_a;
                 if (f->policy != 1) {
@@ -972,7 +1006,8 @@ static int32_t check_filt_args(mrb_filter *f, const void *x, int64_t ldx, int64_
     if (!f) return fail(MRB_ERR_BAD_ARGUMENT, "null handle");
     if (f->device < 0) return fail(MRB_ERR_NO_DEVICE, "host-only handle: no CUDA device bound, and there is no CPU fallback");
     if (n_in < 0 || (n_in > 0 && !x) || ldx < n_in) return fail(MRB_ERR_BAD_ARGUMENT, "bad x / ld_x / n_in");
-    *N = count_outputs(f, n_in, end);          // table kinds: fills (or reuses) the cached schedule f->vn / vphi / va
+    *N = count_outputs(f, n_in, end);          // table kinds: fills (or reuses) the cached schedule store
+    if (*N < 0) return fail(MRB_ERR_CUDA, "out of memory for the schedule");
     if (*N > cap) {
         const char *msg = f->kind == MRB_STANDARD ? "buffer length must be >= x length"                    // :460
                           : f->kind == MRB_INTERPOLATOR ? "length( buffer ) must be >= interpolation * length(x)"  // :503
@@ -1058,6 +1093,7 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
     }
     for (int i = 0; i < nst; ++i) CU(cudaStreamSynchronize(sts[i]));
     f->last_valid = false;                                 // nothing of this handle is in flight any more
+    for (auto &sst : f->sched) sst.pending = false;        // (every stream that read a schedule store has been synchronised)
     commit_state(f, end);
     if (n_in > 0 && f->H > 0) f->cur ^= 1;
     if (n_out) *n_out = N;
@@ -1086,7 +1122,7 @@ extern "C" int32_t mrb_seek(mrb_filter *f, int64_t n0, const void *halo, int64_t
         // (src/Filters.jl:663-673, 780-786), without storing the schedule: ~2 ns per output on the host.
         init_state(f);
         mrb_state e;
-        kk = replay_table(f, n0, &e, nullptr, nullptr, nullptr);
+        kk = replay_table(f, n0, &e, nullptr);
         commit_state(f, e);
         f->sched_valid = false;
     } else {

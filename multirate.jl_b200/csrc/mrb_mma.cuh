@@ -153,7 +153,9 @@ struct alignas(16) MmaParams {
     int KS;                    // K-steps (8 samples) actually issued per group (<= 4 KB)
     int NWB;                   // tile slots in shared memory
     int tile_bytes;            // 2 * KB * G * 128
-    int pad;
+    int nch;                   // channels (rows past it read zero history)
+    const float *hist;         // [nch][H] history of the chunk: samples at x indices -H .. -1
+    long long H;
     long long *prof;           // development aid (MRB_MMA_PROF=1): per CTA 16 counters of cycles spent waiting, see below
 };
 
@@ -169,6 +171,26 @@ struct MmaCfg {
 
 // dynamic shared memory: x ring, tile ring, 2 staging buffers, window starts, 64 mbarrier slots, 1 KiB of alignment slack
 static inline int mma_smem_fixed(int G) { return kMmaNXB * kMmaBoxBytes + 2 * kMmaRows * G * 4 + (kMmaMaxGT + 8) * 4 + 8 * 64 + 1024; }
+
+// The MMAs of one group: KS K-steps of 8 samples, three MMAs each (xh*wh, xh*wl, xl*wh).  Straight-line
+// code with a compile-time trip count: every K-step's operands are (group base) + (constant) and live in uniform
+// registers of their own.  A rolled loop, and an unrolled one with a branch per K-step, both issued an MMA only every
+// ~50 cycles -- each UTCHMMA holds its source uniform registers until the tensor pipe takes it, and the next step's
+// address arithmetic was reusing them; the pipe takes one N = 32 MMA every 16 cycles (tools/mma_probe.cu, T6).
+template <int G, int KS>
+__device__ __forceinline__ void mma_issue_group(uint32_t d, uint32_t a_hi, uint32_t a_lo, int col0, uint64_t bh0, uint32_t lo_off,
+                                                uint32_t idesc) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        int col = col0 + 8 * ks;                                       // 8 ks < RC: one conditional subtraction wraps the ring
+        col -= col >= kMmaRC ? kMmaRC : 0;
+        const uint64_t bh = bh0 + (uint64_t)(((uint32_t)((ks >> 2) * G * 128 + (ks & 3) * 32)) >> 4);
+        const uint64_t bl = bh + lo_off;
+        umma_ts_tf32(d, a_hi + (uint32_t)col, bh, idesc, ks > 0 ? 1u : 0u);
+        umma_ts_tf32(d, a_hi + (uint32_t)col, bl, idesc, 1u);
+        umma_ts_tf32(d, a_lo + (uint32_t)col, bh, idesc, 1u);
+    }
+}
 
 // mbarrier wait that adds the cycles it spent to `acc` when profiling is on
 __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bool prof, long long &acc) {
@@ -239,23 +261,27 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
     const uint32_t tb = *tmem_base_p;
     const bool prof = P.prof != nullptr;
     long long *pr = prof ? P.prof + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
-    long long c0 = 0, c1 = 0, c2 = 0;                                  // cycles this role spent in its waits
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;                                  // cycles this role spent in its waits
     const long long t_start = prof ? clock64() : 0;
 
     mbar_wait(B_GS, 0);                                                // every role needs the window starts
-    const int xbase = gs[0] & ~(kMmaBox - 1);                          // sample index of box 0 of the tile (gstart >= 0 here)
+    // sample index of box 0 of the tile.  It is negative for the tile that holds the chunk's first outputs, whose windows
+    // reach into the history: boxes j < jneg lie wholly before x[0]; the converters fill them from the history buffer
+    // (shiftin!'s carry, src/support.jl:61-80) instead of a TMA box, so no separate head kernel is needed.
+    const int xbase = gs[0] & ~(kMmaBox - 1);
+    const int jneg = xbase < 0 ? (-xbase) / kMmaBox : 0;
     const int jlast = (gs[ng - 1] - xbase + P.KS * 8 - 1) / kMmaBox;   // newest box the tile reads
 
     if (warp == 8) {
         // ---------------- x loader: TMA boxes into the shared-memory ring
         if (elect_one()) {
-            for (int j = 0; j <= jlast; ++j) {
-                const int s = j % NXB;
-                if (j >= NXB) mbar_wait_prof(B_XEMPTY(s), (uint32_t)((j / NXB - 1) & 1), prof, c0);
+            for (int jx = 0; jx + jneg <= jlast; ++jx) {                // jx counts the boxes that come from x
+                const int s = jx % NXB;
+                if (jx >= NXB) mbar_wait_prof(B_XEMPTY(s), (uint32_t)((jx / NXB - 1) & 1), prof, c0);
                 mbar_expect_tx(B_XFULL(s), kMmaBoxBytes);
-                tma_load_2d(smem_u32(xring) + (uint32_t)(s * kMmaBoxBytes), &tmx, xbase + j * kMmaBox, ch0, B_XFULL(s));
+                tma_load_2d(smem_u32(xring) + (uint32_t)(s * kMmaBoxBytes), &tmx, xbase + (jx + jneg) * kMmaBox, ch0, B_XFULL(s));
             }
-            if (prof) { pr[0] = c0; pr[15] = clock64() - t_start; }
+            if (prof) pr[0] = c0;
         }
     } else if (warp == 9) {
         // ---------------- tile loader: one bulk copy per group
@@ -275,55 +301,80 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
         const uint32_t idesc = umma_idesc_tf32(kMmaRows, G);
         const uint32_t lo_off = (uint32_t)(P.KB * G * 128) >> 4;       // hi -> lo half of a tile, in descriptor units
         int boxes_ready = 0, dead = 0;
+        int ar_slot = 0, ws = 0;                                       // a_full slot of box `boxes_ready`, tile slot of group w
+        uint32_t ar_par = 0, w_par = 0;                                //   ... and their phase parities (no divisions in the loop)
+        int a0 = gs[0] - xbase;                                        // multiple of 8
+        long long c4 = 0;
         for (int w = 0; w < ng; ++w) {
-            const int a0 = gs[w] - xbase;                              // multiple of 8
             const int need = (a0 + P.KS * 8 - 1) / kMmaBox;
-            for (; boxes_ready <= need; ++boxes_ready)
-                mbar_wait_prof(B_AFULL(boxes_ready % NAB), (uint32_t)((boxes_ready / NAB) & 1), prof, c0);
-            const int ws = w % P.NWB;
-            mbar_wait_prof(B_WFULL(ws), (uint32_t)((w / P.NWB) & 1), prof, c1);
-            if (w >= 2) mbar_wait_prof(B_DEMPTY(w & 1), (uint32_t)((w / 2 - 1) & 1), prof, c2);
+            const int a0_next = w + 1 < ng ? gs[w + 1] - xbase : 0;
+            const int next_first = w + 1 < ng ? a0_next / kMmaBox : need + 1;
+            for (; boxes_ready <= need; ++boxes_ready) {
+                mbar_wait_prof(B_AFULL(ar_slot), ar_par, prof, c0);
+                if (++ar_slot == NAB) { ar_slot = 0; ar_par ^= 1u; }
+            }
+            mbar_wait_prof(B_WFULL(ws), w_par, prof, c1);
+            if (w >= 2) mbar_wait_prof(B_DEMPTY(w & 1), (uint32_t)(((w >> 1) - 1) & 1), prof, c2);
+            const long long tf0 = prof ? clock64() : 0;
             tc_fence_after();
+            if (prof) c4 += clock64() - tf0;
             const uint32_t d = tb + (uint32_t)(C::TM_D + (w & 1) * G);
             const uint64_t bh0 = umma_desc_sw128(smem_u32(wring) + (uint32_t)(ws * P.tile_bytes));
             const int col0 = a0 % kMmaRC;
+            const long long ti0 = prof ? clock64() : 0;
             if (elect_one()) {
-                // Fully unrolled: every K-step's addresses are (group base) + (compile-time constant), so the uniform
-                // datapath sees short independent chains instead of one loop-carried one (a rolled loop issued an MMA
-                // only every ~53 cycles; the tensor pipe takes one N = 32 MMA every 16).
-#pragma unroll
-                for (int ks = 0; ks < 4 * kMmaMaxKB; ++ks) {
-                    if (ks >= P.KS) break;
-                    int col = col0 + 8 * ks;                             // 8 ks < RC: one conditional subtraction wraps the ring
-                    col -= col >= kMmaRC ? kMmaRC : 0;
-                    const uint64_t bh = bh0 + (uint64_t)(((uint32_t)((ks >> 2) * G * 128 + (ks & 3) * 32)) >> 4);
-                    const uint64_t bl = bh + lo_off;
-                    umma_ts_tf32(d, tb + (uint32_t)(C::TM_AH + col), bh, idesc, ks > 0 ? 1u : 0u);
-                    umma_ts_tf32(d, tb + (uint32_t)(C::TM_AH + col), bl, idesc, 1u);
-                    umma_ts_tf32(d, tb + (uint32_t)(C::TM_AL + col), bh, idesc, 1u);
+                const uint32_t ah = tb + (uint32_t)C::TM_AH, al = tb + (uint32_t)C::TM_AL;
+                switch (P.KS) {                                          // compile-time trip counts: straight-line issue code
+                case 1: mma_issue_group<G, 1>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 2: mma_issue_group<G, 2>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 3: mma_issue_group<G, 3>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 4: mma_issue_group<G, 4>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 5: mma_issue_group<G, 5>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 6: mma_issue_group<G, 6>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 7: mma_issue_group<G, 7>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 8: mma_issue_group<G, 8>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 9: mma_issue_group<G, 9>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 10: mma_issue_group<G, 10>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 11: mma_issue_group<G, 11>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 12: mma_issue_group<G, 12>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 13: mma_issue_group<G, 13>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 14: mma_issue_group<G, 14>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 15: mma_issue_group<G, 15>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 16: mma_issue_group<G, 16>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 17: mma_issue_group<G, 17>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 18: mma_issue_group<G, 18>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 19: mma_issue_group<G, 19>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 20: mma_issue_group<G, 20>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 21: mma_issue_group<G, 21>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 22: mma_issue_group<G, 22>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                case 23: mma_issue_group<G, 23>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                default: mma_issue_group<G, 24>(d, ah, al, col0, bh0, lo_off, idesc); break;
                 }
                 tc_commit(B_WEMPTY(ws));                               // the tile slot may be refilled
                 tc_commit(B_DFULL(w & 1));                             // the accumulators are complete
                 // ring boxes no later group reads: everything before the next group's first box
-                const int next_first = w + 1 < ng ? (gs[w + 1] - xbase) / kMmaBox : need + 1;
                 for (int b = dead; b < next_first; ++b) tc_commit(B_AEMPTY(b % NAB));
             }
             __syncwarp();
-            {
-                const int next_first = w + 1 < ng ? (gs[w + 1] - xbase) / kMmaBox : need + 1;
-                if (next_first > dead) dead = next_first;
-            }
+            if (prof) c3 += clock64() - ti0;
+            if (next_first > dead) dead = next_first;
+            if (++ws == P.NWB) { ws = 0; w_par ^= 1u; }
+            a0 = a0_next;
         }
-        if (prof && lane == 0) { pr[2] = c0; pr[3] = c1; pr[4] = c2; pr[14] = clock64() - t_start; }
+        if (prof && lane == 0) pr[15] = c4;                            // (slot 15: the x loader's total is not reported)
+        if (prof && lane == 0) { pr[2] = c0; pr[3] = c1; pr[4] = c2; pr[11] = c3; pr[14] = clock64() - t_start; }
     } else if (warp >= 4) {
         // ---------------- converters: thread = channel = tensor-memory lane; box j -> columns (j mod NAB) * 32 of both rings
         const int q = warp - 4;                                        // lane quadrant (warp index mod 4)
         const int row = q * 32 + lane;
         const uint32_t lanebase = tb + ((uint32_t)(q * 32) << 16);
         const uint32_t rowpart = ((uint32_t)row * 128u) ^ (((uint32_t)row & 7u) << 4);     // SWIZZLE_128B
+        const bool rowlive = ch0 + row < P.nch;
+        const float *hrow = P.hist + (long long)(ch0 + row) * P.H;
         for (int j = 0; j <= jlast; ++j) {
-            const int s = j % NXB, as = j % NAB;
-            mbar_wait_prof(B_XFULL(s), (uint32_t)((j / NXB) & 1), prof, c0);
+            const int jx = j - jneg;                                   // >= 0: box jx of the x ring; < 0: a history box
+            const int s = jx >= 0 ? jx % NXB : 0, as = j % NAB;
+            if (jx >= 0) mbar_wait_prof(B_XFULL(s), (uint32_t)((jx / NXB) & 1), prof, c0);
             if (j >= NAB) {
                 mbar_wait_prof(B_AEMPTY(as), (uint32_t)((j / NAB - 1) & 1), prof, c1);
                 tc_fence_after();
@@ -332,11 +383,21 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
                 float x[16];
+                if (jx >= 0) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t ad = src + (rowpart ^ ((uint32_t)(hlf * 4 + c) << 4));
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(x[4 * c]), "=f"(x[4 * c + 1]), "=f"(x[4 * c + 2]), "=f"(x[4 * c + 3]) : "r"(ad) : "memory");
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t ad = src + (rowpart ^ ((uint32_t)(hlf * 4 + c) << 4));
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(x[4 * c]), "=f"(x[4 * c + 1]), "=f"(x[4 * c + 2]), "=f"(x[4 * c + 3]) : "r"(ad) : "memory");
+                    }
+                } else {
+                    // samples n = xbase + 32 j + 16 hlf + e < 0: ext index H + n of [history | x]; zero before the history
+                    const int n0 = xbase + j * kMmaBox + hlf * 16;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const long long hi = P.H + n0 + e;
+                        x[e] = (rowlive && hi >= 0) ? __ldg(hrow + hi) : 0.f;
+                    }
                 }
                 uint32_t vh[16], vl[16];
 #pragma unroll
@@ -351,7 +412,7 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(B_AFULL(as));
-            mbar_arrive(B_XEMPTY(s));
+            if (jx >= 0) mbar_arrive(B_XEMPTY(s));
         }
         if (prof && tid == 128) { pr[5] = c0; pr[6] = c1; pr[13] = clock64() - t_start; }
     } else {
@@ -474,32 +535,40 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     const int KB = (int)ceil_div(kneed, 32);
     if (KB > kMmaMaxKB) MRB_MMA_SKIP("window group wider than the tensor-memory ring");
     const int KS = (int)ceil_div(kneed, 8);
-    const int64_t k_begin = (head + GG - 1) / GG * GG;
-    const int64_t groups = ceil_div(cnt, GG), g_begin = k_begin / GG;
-    if (groups - g_begin < 8) MRB_MMA_SKIP("slice too short");
+    // the kernel covers the whole slice: windows that reach into the history are filled from the history buffer
+    (void)head;
+    const int64_t k_begin = 0;
+    const int64_t groups = ceil_div(cnt, GG), g_begin = 0;
+    if (groups < 8) MRB_MMA_SKIP("slice too short");
+    if (G.H > (1ll << 20)) MRB_MMA_SKIP("history too long");
     const int tile_bytes = 2 * KB * GG * 128;
     const int fixed = mma_smem_fixed(GG);
     const int nwb = std::min(4, (p.max_smem - fixed) / tile_bytes);
     if (nwb < 2) MRB_MMA_SKIP("shared memory");
     if (mma_reserve(rw, groups, tile_bytes) != cudaSuccess) return -2;
 
-    {   // pre-pass: one warp per row of every group (rows past the last output are zero)
-        const int64_t nrows = groups * GG;
-        const unsigned gb = (unsigned)ceil_div(nrows, 8);
-        k_mma_tiles<GG><<<gb, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, KB, kind == 5 ? 1 : 0,
-                                            tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt, nrows, rw.d_tiles, rw.d_gstart);
-        ++*launches;
-    }
     MmaParams P{};
     static long long *d_prof = nullptr;
     static const bool want_prof = getenv("MRB_MMA_PROF") != nullptr;
     if (want_prof && !d_prof) { cudaMalloc(&d_prof, 16 * 8 * 4096); cudaMemset(d_prof, 0, 16 * 8 * 4096); }
     P.prof = want_prof ? d_prof : nullptr;
     P.g_begin = g_begin; P.g_end = groups; P.y0 = y0; P.KB = KB; P.KS = KS; P.NWB = nwb; P.tile_bytes = tile_bytes;
+    P.nch = (int)G.nch; P.hist = static_cast<const float *>(G.hist); P.H = G.H;
     const int64_t span = groups - g_begin;
     const int64_t cgroups = ceil_div(G.nch, kMmaRows);
-    // time tiles: one CTA per SM, whole waves where the shape allows, at least 16 groups per tile
-    int64_t tiles = std::max<int64_t>(1, std::min<int64_t>(span / 16, std::max<int64_t>(1, (int64_t)p.num_sms / cgroups)));
+    // time tiles: one CTA per SM (shared and tensor memory), so the grid should be whole waves of num_sms CTAs: take the
+    // tile count that wastes the fewest SM-waves while keeping at least ~48 groups per tile (a CTA's start-up -- tensor
+    // memory allocation, first loads -- costs about as much as 8 groups)
+    int64_t tiles = 1;
+    {
+        const int64_t tmax = std::max<int64_t>(1, span / 48);
+        double best = -1.0;
+        for (int64_t t = 1; t <= std::min<int64_t>(tmax, 4096); ++t) {
+            const int64_t ctas = t * cgroups, waves = ceil_div(ctas, (int64_t)p.num_sms);
+            const double eff = (double)ctas / (double)(waves * p.num_sms) * (1.0 - 8.0 / (8.0 + (double)span / (double)t));
+            if (eff > best + 1e-9) { best = eff; tiles = t; }
+        }
+    }
     if (ceil_div(span, tiles) > kMmaMaxGT) tiles = ceil_div(span, kMmaMaxGT);
     P.GT = (int)ceil_div(span, tiles);
     tiles = ceil_div(span, P.GT);
@@ -520,6 +589,13 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         MRB_MMA_SKIP("y tensor map");
 #undef MRB_MMA_SKIP
+    {   // pre-pass (launched only now: all host-side preparation is done, the two kernels go out back to back): one warp per row of every group (rows past the last output are zero)
+        const int64_t nrows = groups * GG;
+        const unsigned gb = (unsigned)ceil_div(nrows, 8);
+        k_mma_tiles<GG><<<gb, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, KB, kind == 5 ? 1 : 0,
+                                            tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt, nrows, rw.d_tiles, rw.d_gstart);
+        ++*launches;
+    }
     dim3 grid((unsigned)cgroups, (unsigned)tiles);
     k_mma_fir<GG><<<grid, kMmaThreads, fixed + nwb * tile_bytes, st>>>(tmx, tmy, rw.d_tiles, rw.d_gstart, P);
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
@@ -532,9 +608,9 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
             double s[16] = {};
             for (size_t i = 0; i < hp.size(); ++i) s[i % 16] += (double)hp[i] / (double)(cgroups * tiles);
             fprintf(stderr, "[mrb] mma prof (mean cycles per CTA, %lld CTAs, %.0f groups, %.0f boxes): xload wait-empty %.0f | wload wait-empty %.0f | "
-                            "mma wait a_full %.0f w_full %.0f d_empty %.0f total %.0f | conv wait x_full %.0f a_empty %.0f total %.0f | "
+                            "mma wait a_full %.0f w_full %.0f d_empty %.0f fence %.0f issue %.0f total %.0f | conv wait x_full %.0f a_empty %.0f total %.0f | "
                             "epi wait d_full %.0f tma-read %.0f total %.0f\n",
-                    (long long)(cgroups * tiles), s[9], s[10], s[0], s[1], s[2], s[3], s[4], s[14], s[5], s[6], s[13], s[7], s[8], s[12]);
+                    (long long)(cgroups * tiles), s[9], s[10], s[0], s[1], s[2], s[3], s[4], s[15], s[11], s[14], s[5], s[6], s[13], s[7], s[8], s[12]);
         }
     }
     *name = "mma_f32_g32";

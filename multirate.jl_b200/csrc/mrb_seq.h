@@ -48,29 +48,43 @@ struct ArbState {
     double acc;     // phiAccumulator (arbitrary) / Float64 phiIdx (farrow), in [1, Nphi+1)
     int64_t xIdx;   // 1-based
 };
-static inline void arb_update(ArbState &s, double delta, int64_t Nphi) {
-    s.acc += delta;
-    const double nphi = (double)Nphi;
-    if (s.acc > nphi) {
-        const double t = s.acc - 1.0;
-        s.xIdx += (int64_t)(t / nphi);                           // the reference floors the ROUNDED quotient (t > 0)
-        // mod(t, Nphi), exact and bit-identical to fmod on every path (checked against fmod over 8e7 updates of random
-        // rates and Nphi): t - q*Nphi is exact for every integer q with q*Nphi <= t, because Nphi is an integer --
-        // hence a multiple of ulp(t) -- and the difference is no larger than t.  The common quotients are compared
-        // for; otherwise q is estimated with a multiplication and an estimate that is off by one is repaired, exactly
-        // for the same reason.  fmod itself costs ~50 ns and sat on 9 % of the updates of a 0.92 resampler.
-        double r;
-        if (t < nphi) r = t;
-        else if (t < 2.0 * nphi) r = t - nphi;
-        else if (t < 3.0 * nphi) r = t - 2.0 * nphi;
-        else if (t < 9.0e15) {
-            r = t - (double)(int64_t)(t * (1.0 / nphi)) * nphi;
-            if (r < 0.0) r += nphi; else if (r >= nphi) r -= nphi;
-        } else {
-            r = std::fmod(t, nphi);
-        }
-        s.acc = r + 1.0;
+// One update, bit-identical to the reference's
+//     acc += delta; if acc > Nphi { xIdx += ifloor((acc-1)/Nphi); acc = mod(acc-1, Nphi) + 1 }
+// (checked against the literal fmod form over 2e8 updates of random rates and Nphi, rational rates included), but with
+// a dependency chain of two floating-point operations instead of five.  Why it is exact, with a1 = fl(acc + delta) > Nphi:
+//  * t = a1 - 1 is exact (a1 >= 1 is a multiple of its ulp, and so is 1);
+//  * q = floor(t / Nphi) as a real number is found by comparing a1 with 1 + q Nphi; t - q Nphi is exact (Nphi is an
+//    integer, hence a multiple of ulp(t), and the difference is no larger than t);
+//  * (t - q Nphi) + 1 = a1 - q Nphi is a multiple of ulp(a1) no larger than a1, hence representable: the reference's
+//    final "+ 1" never rounds, and acc' = a1 - q Nphi is ONE exact subtraction.
+// The reference floors the ROUNDED quotient fl(t / Nphi) for xIdx, which exceeds q only when t sits within rounding
+// distance below a multiple of Nphi: there (a 2^-48 relative guard band) the division is done for real.
+struct ArbStepper {
+    double delta, nphi, k1, k2, k3, g1, g2, g3;
+    ArbStepper(double delta_, int64_t Nphi) : delta(delta_), nphi((double)Nphi) {
+        k1 = 1.0 + nphi; k2 = 1.0 + 2.0 * nphi; k3 = 1.0 + 3.0 * nphi;
+        const double sh = 1.0 - 0x1p-48;
+        g1 = nphi * sh; g2 = 2.0 * nphi * sh; g3 = 3.0 * nphi * sh;
     }
-}
+    inline void step(ArbState &s) const {
+        const double a1 = s.acc + delta;
+        if (a1 > nphi) {
+            if (a1 < k3) {
+                const double t = a1 - 1.0;
+                if (a1 < k1) { s.acc = a1; s.xIdx += t >= g1 ? (int64_t)(t / nphi) : 0; }
+                else if (a1 < k2) { s.acc = a1 - nphi; s.xIdx += t >= g2 ? (int64_t)(t / nphi) : 1; }
+                else { s.acc = a1 - 2.0 * nphi; s.xIdx += t >= g3 ? (int64_t)(t / nphi) : 2; }
+            } else {                                             // steep decimation: the general form
+                const double t = a1 - 1.0;
+                s.xIdx += (int64_t)(t / nphi);                   // the reference floors the ROUNDED quotient (t > 0)
+                s.acc = std::fmod(t, nphi) + 1.0;
+            }
+        } else {
+            s.acc = a1;
+        }
+    }
+};
+
+static inline void arb_update(ArbState &s, double delta, int64_t Nphi) { ArbStepper(delta, Nphi).step(s); }
 
 }  // namespace mrb

@@ -557,7 +557,8 @@ def test_table_kernel_arbitrary_farrow(tx, polyorder, rate, nch, rng):
         assert states_equal(f, o)
         used.add(f.last_kernel)
     # (float64 below rate 0.5: a step's windows do not fit the shared-memory ring -> generic kernel, by design)
-    assert any(k.startswith("table_") for k in used) or (tx != np.float32 and rate < 0.5), used
+    # float32: the tensor-core kernel (mrb_mma.cuh); float64 / complex64: the table kernel
+    assert any(k.startswith(("table_", "mma_")) for k in used) or (tx != np.float32 and rate < 0.5), used
 
 
 @pytest.mark.parametrize("case", ["rational", "decimator", "interpolator", "standard", "arbitrary", "farrow"])
@@ -571,7 +572,7 @@ def test_host_path_uses_fast_kernels_for_any_length(case, rng):
            "decimator": (Fraction(1, 8), mo.firdes(256, 0.5 / 8, 7.8562).astype(np.float32), np.complex64, "decim"),
            "interpolator": (Fraction(4, 1), mo.firdes(128, 0.5 / 4, 7.8562).astype(np.float32), np.float32, "unit"),
            "standard": (Fraction(1, 1), mo.firdes(128, 0.25, 7.8562).astype(np.float32), np.float32, "unit"),
-           "arbitrary": (0.918734, ha, np.float32, "table"), "farrow": (0.918734, ha, np.float32, "table")}[case]
+           "arbitrary": (0.918734, ha, np.float32, "mma"), "farrow": (0.918734, ha, np.float32, "mma")}[case]
     ratio, h, tx, want = cfg
     extra = (N, 4) if case == "farrow" else (N,) if case == "arbitrary" else ()
     x = rand_samples(rng, (37, 7001), tx)
@@ -671,7 +672,7 @@ def _c_oracle(h, tx, nch, rate, polyorder):
     import c_oracle as co
     pn = None
     if polyorder is not None:
-        pn = mo.pfb2pnfb(mo.taps2pfb(h, 32), polyorder)
+        pn = mr.pfb2pnfb(mr.taps2pfb(h, 32), polyorder)      # coefficients as data: the library's fit on both sides
     return co.COracleFilter("farrow" if polyorder is not None else "arbitrary", h, tx, nch, rate=rate, Nphi=32,
                             polyorder=polyorder or 0, pnfb=pn)
 

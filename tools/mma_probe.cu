@@ -215,20 +215,31 @@ __global__ void __launch_bounds__(160, 1) k_probe(const ProbeArgs P) {
 
 // Issue-rate probe: the whole warp enters, one ELECTED lane issues (ptxas then keeps the operands in uniform
 // registers without a divergence waterfall).  NACC independent accumulators are used round robin.
+// Variants (flags): 1 = tcgen05.commit after every 48 MMAs (one "group", as the FIR kernel does);
+//   2 = the FIR kernel's tensor-memory layout (D at columns 0..63, A rings at 64.. and 288..);
+//   4 = warps 0-3 hammer tcgen05.st into unrelated columns meanwhile;  8 = warps 0-3 hammer tcgen05.ld of D meanwhile;
+//   16 = non-zero data in B (shared memory) and A (tensor memory).
 template <int N, bool TS, int NACC>
-__global__ void __launch_bounds__(160, 1) k_rate(long long *cycles, int reps) {
+__global__ void __launch_bounds__(160, 1) k_rate(long long *cycles, int reps, int flags) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) unsigned long long bar2;
+    __shared__ volatile int stop;
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    for (int i = tid; i < 3 * 65536 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    const int lane = tid & 31;
+    for (int i = tid; i < 3 * 65536 / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(smem)[i] = (flags & 16) ? make_uint4(0x3f800000u + 8192u * (i & 63), 0x3f000000u, 0xbf800000u + 8192u * (i & 7), 0x3e000000u)
+                                                           : make_uint4(0, 0, 0, 0);
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
+        stop = 0;
         mbar_init(smem_u32(&bar), 1);
+        mbar_init(smem_u32(&bar2), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -236,6 +247,20 @@ __global__ void __launch_bounds__(160, 1) k_rate(long long *cycles, int reps) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tb = tmem_base_s;
+    const uint32_t colD = 0, colAh = (flags & 2) ? 64 : 256, colAl = (flags & 2) ? 288 : 384;
+    if (warp < 4 && (flags & 16)) {
+        const uint32_t lanebase = tb + ((uint32_t)(warp * 32) << 16);
+        for (int c = 64; c < 512; c += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0x3f800000u + 8192u * (uint32_t)((c + e + lane) & 63);
+            st32(lanebase + c, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     if (warp == 4) {
         const uint32_t idesc = make_idesc(128, N);
         const uint32_t sb = smem_u32(smem);
@@ -246,12 +271,12 @@ __global__ void __launch_bounds__(160, 1) k_rate(long long *cycles, int reps) {
             for (int ks = 0; ks < 16; ++ks) {
                 const uint32_t boff = (uint32_t)((ks >> 2) * N * 128 + (ks & 3) * 32) >> 4;
                 const uint32_t aoff = (uint32_t)((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4;
-                const uint32_t d = tb + (uint32_t)((ks % NACC) * N);                 // D tiles: columns [0, NACC*N)
+                const uint32_t d = tb + colD + (uint32_t)((ks % NACC) * N);
                 if (elect_one()) {
                     if (TS) {
-                        mma_ts(d, tb + 256 + 8 * ks, bdesc0 + boff, idesc, 1u);
-                        mma_ts(d, tb + 256 + 8 * ks, bdesc0 + boff + 4096, idesc, 1u);
-                        mma_ts(d, tb + 384 + 8 * ks, bdesc0 + boff, idesc, 1u);
+                        mma_ts(d, tb + colAh + 8 * ks, bdesc0 + boff, idesc, 1u);
+                        mma_ts(d, tb + colAh + 8 * ks, bdesc0 + boff + 4096, idesc, 1u);
+                        mma_ts(d, tb + colAl + 8 * ks, bdesc0 + boff, idesc, 1u);
                     } else {
                         mma_ss(d, adesc0 + aoff, bdesc0 + boff, idesc, 1u);
                         mma_ss(d, adesc0 + aoff, bdesc0 + boff + 4096, idesc, 1u);
@@ -260,12 +285,26 @@ __global__ void __launch_bounds__(160, 1) k_rate(long long *cycles, int reps) {
                 }
                 __syncwarp();
             }
+            if ((flags & 1) && r + 1 < reps) {
+                if (elect_one()) tc_commit(smem_u32(&bar2));          // nobody waits on bar2: its phase just keeps flipping
+                __syncwarp();
+            }
         }
         if (elect_one()) tc_commit(smem_u32(&bar));
         __syncwarp();
+        // with per-group commits the barrier has flipped many times: wait for the LAST MMA by polling both parities
         mbar_wait(smem_u32(&bar), 0);
         long long t1 = clock64();
         if (tid == 128) cycles[0] = t1 - t0;
+        if (tid == 128) stop = 1;
+    } else if (flags & (4 | 8)) {
+        const uint32_t lanebase = tb + ((uint32_t)(warp * 32) << 16);
+        uint32_t v[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+        while (!stop) {
+            if (flags & 4) { st32(lanebase + 200, v); asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+            if (flags & 8) { ld32(lanebase + 32, v); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+        }
+        if (v[0] == 0xdeadbeef) cycles[1] = v[1];
     }
     tc_fence_before();
     __syncthreads();
@@ -273,16 +312,16 @@ __global__ void __launch_bounds__(160, 1) k_rate(long long *cycles, int reps) {
 }
 
 template <int N, bool TS, int NACC>
-static int rate(long long *dcyc, const char *what) {
+static int rate(long long *dcyc, const char *what, int flags = 0) {
     const int SMEM = 3 * 65536, reps = 64;
     if (cudaFuncSetAttribute(k_rate<N, TS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return 1;
     long long cyc = 0;
     for (int it = 0; it < 2; ++it) {
-        k_rate<N, TS, NACC><<<1, 160, SMEM>>>(dcyc, reps);
+        k_rate<N, TS, NACC><<<1, 160, SMEM>>>(dcyc, reps, flags);
         if (cudaDeviceSynchronize() != cudaSuccess) { printf("k_rate failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
         cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost);
     }
-    printf("T6 %s N=%3d accumulators=%d: %.1f cycles per MMA (M128 x N x K8, %d MMAs)\n", what, N, NACC, (double)cyc / (reps * 48), reps * 48);
+    printf("T6 %s N=%3d accumulators=%d flags=%2d: %.1f cycles per MMA (M128 x N x K8, %d MMAs)\n", what, N, NACC, flags, (double)cyc / (reps * 48), reps * 48);
     return 0;
 }
 
@@ -388,10 +427,11 @@ int main() {
         if (run(5, N, 1, false, reps, &err, &cyc)) return 1;
         printf("T5 SS timing N=%3d: %lld cycles for %d MMAs (M128 K8) = %.1f cycles/MMA\n", N, cyc, reps * 16 * 3, (double)cyc / (reps * 16 * 3));
     }
-    if (rate<16, true, 1>(dcyc, "TS") || rate<16, true, 4>(dcyc, "TS") || rate<32, true, 1>(dcyc, "TS") || rate<32, true, 4>(dcyc, "TS") ||
-        rate<64, true, 1>(dcyc, "TS") || rate<64, true, 2>(dcyc, "TS") || rate<128, true, 1>(dcyc, "TS") || rate<256, true, 1>(dcyc, "TS") ||
-        rate<16, false, 1>(dcyc, "SS") || rate<32, false, 1>(dcyc, "SS") || rate<32, false, 4>(dcyc, "SS") || rate<64, false, 1>(dcyc, "SS") ||
-        rate<128, false, 1>(dcyc, "SS") || rate<256, false, 1>(dcyc, "SS"))
+    if (rate<32, true, 1>(dcyc, "TS", 0) || rate<32, true, 1>(dcyc, "TS", 1) || rate<32, true, 1>(dcyc, "TS", 2) ||
+        rate<32, true, 1>(dcyc, "TS", 4) || rate<32, true, 1>(dcyc, "TS", 8) || rate<32, true, 1>(dcyc, "TS", 16) ||
+        rate<32, true, 1>(dcyc, "TS", 18) || rate<32, true, 1>(dcyc, "TS", 31) || rate<32, true, 2>(dcyc, "TS", 31) ||
+        rate<16, true, 1>(dcyc, "TS", 16) || rate<64, true, 1>(dcyc, "TS", 16) || rate<128, true, 1>(dcyc, "TS", 16) ||
+        rate<32, false, 1>(dcyc, "SS", 16) || rate<128, false, 1>(dcyc, "SS", 16))
         return 1;
     return 0;
 }
