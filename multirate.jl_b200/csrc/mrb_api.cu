@@ -915,7 +915,21 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
             P.mode = SEQ_INTEGER; P.L = f->L; P.M = f->M; P.p0 = f->phiIdx - 1; P.d0m1 = f->deficit - 1;
             P.k_base = 0; P.nout = N;
             int64_t k_begin = -1;
-            if (f->policy != 1) {
+            if (f->policy == 0 && f->mma.ok) {
+                // tensor cores (float32 samples and taps): a group of 32 outputs spans at most floor(31 M / L) + 1 inputs
+                static const bool mma_int = !(getenv("MRB_MMA_INT") && atoi(getenv("MRB_MMA_INT")) == 0);
+                // short single-rate filters are HBM bound on the CUDA cores already (standard, 32 taps: k_unit_f32 730 Gout/s,
+                // tensor-core kernel 592); from ~48 taps on the tensor cores win (128 taps: 438 against 227)
+                const bool unit_better = f->unit.ok && f->L == 1 && f->M == 1 && f->T <= 48;
+                if (mma_int && !unit_better) {
+                    MmaSched S{};
+                    S.mode = 2; S.L = f->L; S.M = f->M; S.p0 = P.p0; S.d0m1 = P.d0m1; S.k_base = 0;
+                    k_begin = mma_try_launch(f->mma, f->tctx[ctx].mrows, P, S, 0, f->d_bank, nullptr, nullptr, 0, N,
+                                             (31 * f->M) / f->L + 1, st, &f->last_kernel, &f->launches);
+                    if (k_begin == -2) return fail(MRB_ERR_CUDA, "tensor-core launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                }
+            }
+            if (k_begin == -1 && f->policy != 1) {
                 k_begin = tiled_try_launch(f->tiled, P, st, &f->last_kernel, &f->launches);
                 if (k_begin == -1) k_begin = unit_try_launch(f->unit, P, st, &f->last_kernel, &f->launches);
                 if (k_begin == -1) k_begin = decim_try_launch(f->decim, P, st, &f->last_kernel, &f->launches);
@@ -957,8 +971,10 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                         int64_t gs32 = 0;                      // widest spread of window starts inside a group of 32 outputs
                         for (int64_t g0 = 0; g0 < cnt; g0 += kMmaG)
                             gs32 = std::max(gs32, vn[k0 + std::min<int64_t>(g0 + kMmaG, cnt) - 1] - vn[k0 + g0]);
-                        kb = mma_try_launch(f->mma, tc.mrows, P, f->kind, f->polyorder + 1, f->th == MRB_F32, f->d_bank, f->d_dbank,
-                                            f->d_pnfb, k0, cnt, head, gs32, st, &f->last_kernel, &f->launches);
+                        MmaSched S{};
+                        S.mode = f->kind == MRB_FARROW ? 1 : 0; S.sn = s.d_n; S.sphi = s.d_phi; S.sa = s.d_a;
+                        kb = mma_try_launch(f->mma, tc.mrows, P, S, f->polyorder + 1, f->d_bank, f->d_dbank, f->d_pnfb, k0, cnt, gs32, st,
+                                            &f->last_kernel, &f->launches);
                         if (kb == -2) return fail(MRB_ERR_CUDA, "tensor-core launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                     }
                     int64_t gspan = 0;                         // widest spread of window starts inside a group of 8 outputs

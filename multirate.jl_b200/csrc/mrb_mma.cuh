@@ -98,41 +98,75 @@ __device__ __forceinline__ float tf32_rna(float x) {
 //   row r, index j = tap (j - d) of output gG+r,  d = (sn[k] - H) - gstart[g]   (zero outside the T taps)
 // `mode`: 0 arbitrary (pfb + alpha*dpfb), 1 farrow (Horner), 2 integer schedule (branch sphi[k] of pfb, no blend)
 // ---------------------------------------------------------------------------------------------------------
+struct MmaSched {               // where the pre-pass takes an output's (window end, branch, blend) from
+    int mode;                   // 0 arbitrary (pfb + alpha*dpfb), 1 farrow (Horner), 2 integer schedule (closed form)
+    const int64_t *sn;          // modes 0/1: 0-based x index of the window's last sample, per output of the slice
+    const int32_t *sphi;        // mode 0: 0-based branch
+    const double *sa;           // mode 0: alpha; mode 1: Float64 phase
+    long long L, M, p0, d0m1;   // mode 2: n_k = d0m1 + (p0 + k M) / L, branch (p0 + k M) % L   (k = slice-relative + k_base)
+    long long k_base;
+};
+
+__device__ __forceinline__ void mma_sched_at(const MmaSched &S, int64_t k, int64_t &n, int64_t &phi) {
+    if (S.mode == 2) {
+        const long long t = S.p0 + (S.k_base + k) * S.M;
+        const long long q = t / S.L;
+        n = S.d0m1 + q;
+        phi = t - q * S.L;
+    } else {
+        n = S.sn[k];
+        phi = S.mode == 0 ? S.sphi[k] : 0;
+    }
+}
+
+// Rows [0, nrows) of the tile table (nrows = tiles * G; for periodic integer schedules only one period of tiles is
+// built) and the window starts of ALL ngroups groups.  `nout`: rows at or past it are zero (aperiodic tables only).
 template <int G>
 __global__ void __launch_bounds__(256)
 k_mma_tiles(const float *__restrict__ pfb, const float *__restrict__ dpfb, const double *__restrict__ pnfb, int P1, int T, int KB,
-            int mode, int tap_is_f32, const int64_t *__restrict__ sn, const int32_t *__restrict__ sphi,
-            const double *__restrict__ sa, int64_t H, int64_t nout, int64_t nrows, float *__restrict__ tiles,
+            const MmaSched S, int64_t H, int64_t nout, int64_t nrows, int64_t ngroups, float *__restrict__ tiles,
             int32_t *__restrict__ gstart) {
+    {   // window starts: one thread per group
+        const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+        if (g < ngroups) {
+            int64_t n, phi;
+            mma_sched_at(S, g * G, n, phi);
+            const int64_t xg = n - H;
+            gstart[g] = (int32_t)(xg >= 0 ? (xg & ~(int64_t)7) : -(((-xg) + 7) & ~(int64_t)7));
+        }
+    }
     const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (k >= nrows) return;                                          // nrows = groups * G
+    if (k >= nrows) return;
     const int lane = threadIdx.x & 31;
     const int64_t g = k / G;
     const int r = (int)(k - g * G);
-    const int64_t xg = sn[g * G] - H;                                // the group's first output exists (g*G < nout)
+    int64_t ng0, phig;
+    mma_sched_at(S, g * G, ng0, phig);
+    const int64_t xg = ng0 - H;
     const int64_t al = xg >= 0 ? (xg & ~(int64_t)7) : -(((-xg) + 7) & ~(int64_t)7);
-    if (r == 0 && lane == 0) gstart[g] = (int32_t)al;
     const bool live = k < nout;
-    const int d = live ? (int)(sn[k] - H - al) : 0;
-    const double ph = live && mode != 2 ? sa[k] : 0.0;               // farrow: phase; arbitrary: alpha
-    const int64_t obase = (live && mode != 1) ? (int64_t)sphi[k] * T : 0;
+    int64_t nk = 0, phik = 0;
+    if (live) mma_sched_at(S, k, nk, phik);
+    const int d = live ? (int)(nk - H - al) : 0;
+    const double ph = live && S.mode != 2 ? S.sa[k] : 0.0;           // farrow: phase; arbitrary: alpha
+    const int64_t obase = phik * T;
     const int64_t tile_floats = (int64_t)2 * KB * G * 32;
     float *th = tiles + g * tile_floats, *tl = th + (int64_t)KB * G * 32;
     for (int j = lane; j < KB * 32; j += 32) {
         const int i = j - d;
         float v = 0.f;
         if (live && i >= 0 && i < T) {
-            if (mode == 1) {
+            if (S.mode == 1) {
                 // currentTaps[i] = polyval(pnfb[i], phase): Horner highest order first in Float64, separately rounded
                 // multiply and add, rounded to the tap type (src/Filters.jl:789-791)
                 const double *c = pnfb + (int64_t)i * P1;
                 double a = c[P1 - 1];
                 for (int p = P1 - 2; p >= 0; --p) a = __dadd_rn(__dmul_rn(a, ph), c[p]);
                 v = (float)a;
-            } else if (mode == 0) {
+            } else if (S.mode == 0) {
                 v = (float)((double)pfb[obase + i] + ph * (double)dpfb[obase + i]);   // tapsforphase, :681-686
             } else {
-                v = pfb[obase + i];
+                v = pfb[obase + i];                                                     // pfb[:, phi], :558-565
             }
         }
         const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
@@ -153,6 +187,8 @@ struct alignas(16) MmaParams {
     int KS;                    // K-steps (8 samples) actually issued per group (<= 4 KB)
     int NWB;                   // tile slots in shared memory
     int tile_bytes;            // 2 * KB * G * 128
+    int period;                // tile of group g = tile (g mod period): g_end - 0 for aperiodic tables
+    int resident;              // period <= NWB: every tile is loaded once and stays in its slot
     int nch;                   // channels (rows past it read zero history)
     const float *hist;         // [nch][H] history of the chunk: samples at x indices -H .. -1
     long long H;
@@ -284,15 +320,25 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
             if (prof) pr[0] = c0;
         }
     } else if (warp == 9) {
-        // ---------------- tile loader: one bulk copy per group
+        // ---------------- tile loader: one bulk copy per group; a periodic schedule with few distinct tiles (standard,
+        // interpolator: one) keeps them all resident instead
         if (elect_one()) {
-            for (int w = 0; w < ng; ++w) {
-                const int s = w % P.NWB;
-                if (w >= P.NWB) mbar_wait_prof(B_WEMPTY(s), (uint32_t)((w / P.NWB - 1) & 1), prof, c0);
-                mbar_expect_tx(B_WFULL(s), (uint32_t)P.tile_bytes);
-                bulk_load(smem_u32(wring) + (uint32_t)(s * P.tile_bytes),
-                          reinterpret_cast<const unsigned char *>(tiles) + (size_t)(g0 + w) * (size_t)P.tile_bytes,
-                          (uint32_t)P.tile_bytes, B_WFULL(s));
+            if (P.resident) {
+                for (int t = 0; t < P.period; ++t) {
+                    mbar_expect_tx(B_WFULL(t), (uint32_t)P.tile_bytes);
+                    bulk_load(smem_u32(wring) + (uint32_t)(t * P.tile_bytes),
+                              reinterpret_cast<const unsigned char *>(tiles) + (size_t)t * (size_t)P.tile_bytes, (uint32_t)P.tile_bytes, B_WFULL(t));
+                }
+            } else {
+                int ti = (int)(g0 % P.period);
+                for (int w = 0; w < ng; ++w) {
+                    const int s = w % P.NWB;
+                    if (w >= P.NWB) mbar_wait_prof(B_WEMPTY(s), (uint32_t)((w / P.NWB - 1) & 1), prof, c0);
+                    mbar_expect_tx(B_WFULL(s), (uint32_t)P.tile_bytes);
+                    bulk_load(smem_u32(wring) + (uint32_t)(s * P.tile_bytes),
+                              reinterpret_cast<const unsigned char *>(tiles) + (size_t)ti * (size_t)P.tile_bytes, (uint32_t)P.tile_bytes, B_WFULL(s));
+                    if (++ti == P.period) ti = 0;
+                }
             }
             if (prof) pr[1] = c0;
         }
@@ -301,8 +347,9 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
         const uint32_t idesc = umma_idesc_tf32(kMmaRows, G);
         const uint32_t lo_off = (uint32_t)(P.KB * G * 128) >> 4;       // hi -> lo half of a tile, in descriptor units
         int boxes_ready = 0, dead = 0;
-        int ar_slot = 0, ws = 0;                                       // a_full slot of box `boxes_ready`, tile slot of group w
+        int ar_slot = 0, ws = P.resident ? (int)(g0 % P.period) : 0;    // a_full slot of box `boxes_ready`, tile slot of group w
         uint32_t ar_par = 0, w_par = 0;                                //   ... and their phase parities (no divisions in the loop)
+        const int ws_wrap = P.resident ? P.period : P.NWB;
         int a0 = gs[0] - xbase;                                        // multiple of 8
         long long c4 = 0;
         for (int w = 0; w < ng; ++w) {
@@ -358,7 +405,7 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
             __syncwarp();
             if (prof) c3 += clock64() - ti0;
             if (next_first > dead) dead = next_first;
-            if (++ws == P.NWB) { ws = 0; w_par ^= 1u; }
+            if (++ws == ws_wrap) { ws = 0; if (!P.resident) w_par ^= 1u; }   // resident tiles: phase 0 stays complete
             a0 = a0_next;
         }
         if (prof && lane == 0) pr[15] = c4;                            // (slot 15: the x loader's total is not reported)
@@ -467,7 +514,7 @@ constexpr int kMmaG = 32;
 struct MmaRows {                       // per pipeline stream (TableCtx): the tap tiles and window starts of one slice
     float *d_tiles = nullptr;
     int32_t *d_gstart = nullptr;
-    int64_t cap_groups = 0;
+    int64_t cap_tiles = 0, cap_groups = 0;
     int64_t tile_bytes = 0;
 };
 
@@ -486,11 +533,11 @@ struct MmaPlan {
 
 static inline void mma_release(MmaPlan &p) { p.ok = false; }
 
-// kind/tx/ty are the mrb.h enums (4 arbitrary, 5 farrow ; 0 = float32)
+// kind/tx/ty/th are the mrb.h enums (0 standard, 1 interpolator, 2 decimator, 3 rational, 4 arbitrary, 5 farrow; 0 = float32)
 static inline int32_t mma_prepare(MmaPlan &p, int kind, int tx, int ty, int th, int64_t T, const cudaDeviceProp &prop) {
     p.ok = false;
     static const bool off = getenv("MRB_NO_MMA") != nullptr;
-    if (off || !(kind == 4 || kind == 5) || tx != 0 || ty != 0 || th != 0) return 0;
+    if (off || kind < 0 || kind > 5 || tx != 0 || ty != 0 || th != 0) return 0;
     if (T + 7 > kMmaMaxKB * 32) return 0;
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -506,24 +553,24 @@ static inline int32_t mma_prepare(MmaPlan &p, int kind, int tx, int ty, int th, 
     return 0;
 }
 
-static inline cudaError_t mma_reserve(MmaRows &r, int64_t groups, int64_t tile_bytes) {
-    if (r.cap_groups >= groups && r.tile_bytes == tile_bytes) return cudaSuccess;
+static inline cudaError_t mma_reserve(MmaRows &r, int64_t ntiles, int64_t groups, int64_t tile_bytes) {
+    if (r.cap_tiles >= ntiles && r.cap_groups >= groups && r.tile_bytes == tile_bytes) return cudaSuccess;
     mmarows_release(r);
-    cudaError_t e = cudaMalloc(&r.d_tiles, (size_t)groups * (size_t)tile_bytes);
+    cudaError_t e = cudaMalloc(&r.d_tiles, (size_t)ntiles * (size_t)tile_bytes);
     if (e != cudaSuccess) return e;
     e = cudaMalloc(&r.d_gstart, (size_t)(groups + 8) * sizeof(int32_t));
     if (e != cudaSuccess) return e;
-    r.cap_groups = groups; r.tile_bytes = tile_bytes;
+    r.cap_tiles = ntiles; r.cap_groups = groups; r.tile_bytes = tile_bytes;
     return cudaSuccess;
 }
 
-// One schedule slice: outputs [0, cnt) (y index y0 + k), the first `head` of which have windows that reach into the
-// history; max_group_span = widest spread of window starts inside a group of kMmaG outputs.  Builds the tap tiles, then
-// launches the main kernel for the groups from the first whole group behind the head.  Returns the first output the
-// kernel covers (the caller computes the outputs before it with the generic kernel), -1 when not covered, -2 on error.
-static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G, int kind, int P1, int tap_is_f32,
+// One schedule slice: outputs [0, cnt) of the slice (y index y0 + k).  `S` says where the schedule comes from (uploaded
+// arrays for the arbitrary-rate kinds, the closed form for the integer kinds); max_group_span = widest spread of window
+// starts inside a group of kMmaG outputs.  Builds the tap tiles, then launches the main kernel for the whole slice
+// (chunk head included).  Returns 0 (the first output covered), -1 when not covered, -2 on a CUDA error.
+static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G, const MmaSched &S, int P1,
                                      const void *d_pfb, const void *d_dpfb, const double *d_pnfb, int64_t y0, int64_t cnt,
-                                     int64_t head, int64_t max_group_span, cudaStream_t st, const char **name, int64_t *launches) {
+                                     int64_t max_group_span, cudaStream_t st, const char **name, int64_t *launches) {
     static const bool trace = getenv("MRB_TRACE") != nullptr;
 #define MRB_MMA_SKIP(why) do { if (trace) fprintf(stderr, "[mrb] tensor-core kernel not used: %s\n", why); return -1; } while (0)
     if (!p.ok) MRB_MMA_SKIP("configuration not covered");
@@ -536,7 +583,6 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     if (KB > kMmaMaxKB) MRB_MMA_SKIP("window group wider than the tensor-memory ring");
     const int KS = (int)ceil_div(kneed, 8);
     // the kernel covers the whole slice: windows that reach into the history are filled from the history buffer
-    (void)head;
     const int64_t k_begin = 0;
     const int64_t groups = ceil_div(cnt, GG), g_begin = 0;
     if (groups < 8) MRB_MMA_SKIP("slice too short");
@@ -545,7 +591,17 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     const int fixed = mma_smem_fixed(GG);
     const int nwb = std::min(4, (p.max_smem - fixed) / tile_bytes);
     if (nwb < 2) MRB_MMA_SKIP("shared memory");
-    if (mma_reserve(rw, groups, tile_bytes) != cudaSuccess) return -2;
+    // Integer schedules repeat: group g + P reads the same taps at the same alignment as group g once P groups advance the
+    // phase by a multiple of L and the input by a multiple of 8 samples.  Only one period of tiles is built (standard and
+    // interpolators: ONE tile, kept resident in shared memory; 147//160: 147 tiles, L2 resident).
+    int64_t period = groups;
+    if (S.mode == 2) {
+        for (int64_t q = 1; q <= std::min<int64_t>(groups, 8 * S.L); ++q)
+            if ((q * GG * S.M) % S.L == 0 && ((q * GG * S.M) / S.L) % 8 == 0) { period = q; break; }
+    }
+    const int64_t ntiles = std::min(period, groups);
+    const bool resident = S.mode == 2 && period <= nwb;
+    if (mma_reserve(rw, ntiles, groups, tile_bytes) != cudaSuccess) return -2;
 
     MmaParams P{};
     static long long *d_prof = nullptr;
@@ -553,6 +609,7 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     if (want_prof && !d_prof) { cudaMalloc(&d_prof, 16 * 8 * 4096); cudaMemset(d_prof, 0, 16 * 8 * 4096); }
     P.prof = want_prof ? d_prof : nullptr;
     P.g_begin = g_begin; P.g_end = groups; P.y0 = y0; P.KB = KB; P.KS = KS; P.NWB = nwb; P.tile_bytes = tile_bytes;
+    P.period = (int)ntiles; P.resident = resident ? 1 : 0;
     P.nch = (int)G.nch; P.hist = static_cast<const float *>(G.hist); P.H = G.H;
     const int64_t span = groups - g_begin;
     const int64_t cgroups = ceil_div(G.nch, kMmaRows);
@@ -589,11 +646,12 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         MRB_MMA_SKIP("y tensor map");
 #undef MRB_MMA_SKIP
-    {   // pre-pass (launched only now: all host-side preparation is done, the two kernels go out back to back): one warp per row of every group (rows past the last output are zero)
-        const int64_t nrows = groups * GG;
-        const unsigned gb = (unsigned)ceil_div(nrows, 8);
-        k_mma_tiles<GG><<<gb, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, KB, kind == 5 ? 1 : 0,
-                                            tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt, nrows, rw.d_tiles, rw.d_gstart);
+    {   // pre-pass (launched only now: all host-side preparation is done, the two kernels go out back to back): one warp
+        // per tile row (rows past the last output are zero) and one thread per group for its window start
+        const int64_t nrows = ntiles * GG;
+        const unsigned gb = (unsigned)std::max(ceil_div(nrows, 8), ceil_div(groups, 256));
+        k_mma_tiles<GG><<<gb, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, KB, S, G.H,
+                                            S.mode == 2 ? nrows : cnt, nrows, groups, rw.d_tiles, rw.d_gstart);
         ++*launches;
     }
     dim3 grid((unsigned)cgroups, (unsigned)tiles);
@@ -613,7 +671,7 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
                     (long long)(cgroups * tiles), s[9], s[10], s[0], s[1], s[2], s[3], s[4], s[15], s[11], s[14], s[5], s[6], s[13], s[7], s[8], s[12]);
         }
     }
-    *name = "mma_f32_g32";
+    *name = resident ? "mma_f32_g32_resident" : "mma_f32_g32";
     ++*launches;
     return k_begin;
 }

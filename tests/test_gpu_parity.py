@@ -403,7 +403,8 @@ def test_unit_stride_f32_kernel_shapes(L, ntaps, nch, tx, rng):
     n = 5000                                                          # row pitch: a multiple of 16 bytes (TMA)
     x = rand_samples(rng, (nch, n), tx)
     xd = torch.from_numpy(x).cuda()
-    f = mr.FIRFilter(h, ratio)
+    f = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
+    f.set_kernel_policy(2)                                            # the CUDA-core fast paths (float32 would take the tensor-core kernel)
     g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
     g.set_kernel_policy(1)
     o = mo.FIRFilter(h, ratio)
@@ -570,8 +571,8 @@ def test_host_path_uses_fast_kernels_for_any_length(case, rng):
     ha = (mo.firdes(-(-hl // N) * N, 0.45, beta, samplerate=32) * N).astype(np.float32)
     cfg = {"rational": (Fraction(147, 160), mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32), np.complex64, "tiled"),
            "decimator": (Fraction(1, 8), mo.firdes(256, 0.5 / 8, 7.8562).astype(np.float32), np.complex64, "decim"),
-           "interpolator": (Fraction(4, 1), mo.firdes(128, 0.5 / 4, 7.8562).astype(np.float32), np.float32, "unit"),
-           "standard": (Fraction(1, 1), mo.firdes(128, 0.25, 7.8562).astype(np.float32), np.float32, "unit"),
+           "interpolator": (Fraction(4, 1), mo.firdes(128, 0.5 / 4, 7.8562).astype(np.float32), np.float32, "mma"),
+           "standard": (Fraction(1, 1), mo.firdes(128, 0.25, 7.8562).astype(np.float32), np.float32, "mma"),
            "arbitrary": (0.918734, ha, np.float32, "mma"), "farrow": (0.918734, ha, np.float32, "mma")}[case]
     ratio, h, tx, want = cfg
     extra = (N, 4) if case == "farrow" else (N,) if case == "arbitrary" else ()
@@ -625,6 +626,8 @@ def test_fast_paths_random_stress_against_generic_kernel(rng):
         n = 4 * int(r.integers(1500, 3000))
         x = torch.from_numpy(rand_samples(r, (nch, n), tx)).cuda()
         f = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
+        if want in ("unit", "decim_f32"):
+            f.set_kernel_policy(2)                                 # float32: keep to the CUDA-core fast paths here
         g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
         g.set_kernel_policy(1)
         cut = sorted(4 * int(v) for v in r.integers(1, n // 4, size=2))
@@ -760,3 +763,37 @@ def test_setphase_one_before_first_filt(rng):
     y, w = f.filt(x), o.filt(x)
     assert y.shape == w.shape and nerr(y, w) <= 1e-5
     assert states_equal(f, o)
+
+
+@pytest.mark.parametrize("ratio,ntaps,nch", [(Fraction(1, 1), 128, 140), (Fraction(1, 1), 150, 5), (Fraction(1, 1), 60, 128), (Fraction(4, 1), 128, 33),
+                                              (Fraction(5, 1), 300, 200), (Fraction(147, 160), 3528, 129), (Fraction(160, 147), 3840, 64),
+                                              (Fraction(3, 2), 100, 31), (Fraction(5, 7), 333, 300), (Fraction(2, 1), 9, 1), (Fraction(1, 2), 100, 77),
+                                              (Fraction(1, 3), 40, 256)])
+def test_tensor_core_kernel_integer_ratios(ratio, ntaps, nch, rng):
+    """mrb_mma.cuh on the integer-ratio kinds (float32 samples and taps): standard, interpolator, rational and gentle
+    decimators run as banded tcgen05 products with 3xTF32 (the K5 experiment of SURVEY 7).  Periodic schedules build one
+    period of tap tiles (ONE resident tile for standard / interpolators).  Ragged taps and channels, streamed chunks with
+    carried phase / deficit and a chunk head that reaches into the history, odd chunk lengths (-> other kernels): against
+    the oracle (float64 accumulation) and the generic kernel; counts and state exact."""
+    import torch
+    h = rng.standard_normal(ntaps).astype(np.float32)
+    n = 9000
+    x = rand_samples(rng, (nch, n), np.float32)
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=np.float32)
+    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=np.float32)
+    g.set_kernel_policy(1)
+    o = mo.FIRFilter(h, ratio)
+    used = set()
+    for a, b in ((0, 4000), (4000, 4004), (4004, 6001), (6001, 6008), (6008, n)):
+        yd, yg = f.filt(xd[:, a:b]), g.filt(xd[:, a:b])
+        w = o.filt(x[: min(nch, 3), a:b])
+        torch.cuda.synchronize()
+        y = yd.cpu().numpy()
+        assert y.shape == (nch, w.shape[1])
+        if w.size:
+            assert nerr(y[: min(nch, 3)], w) <= 1e-5, (a, b, nerr(y[: min(nch, 3)], w), f.last_kernel)
+            assert nerr(yg.cpu().numpy(), y) <= 4e-6, (a, b, f.last_kernel)
+        assert states_equal(f, o)
+        used.add(f.last_kernel)
+    assert any(k.startswith("mma_") for k in used), used
