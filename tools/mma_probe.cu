@@ -297,6 +297,24 @@ __global__ void __launch_bounds__(160, 1) k_rate(long long *cycles, int reps, in
         long long t1 = clock64();
         if (tid == 128) cycles[0] = t1 - t0;
         if (tid == 128) stop = 1;
+    } else if (flags & (32 | 64)) {
+        // shared-memory traffic from the other warps: 32 = conflict-free LDS.128 + STS.128 on another region (what the
+        // converter / epilogue warps of the FIR kernel do); 64 = only every 8th pass (lighter)
+        unsigned char *scratch = smem + 160 * 1024;
+        const uint32_t base = smem_u32(scratch) + (uint32_t)(tid * 16);
+        float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+        int it = 0;
+        while (!stop) {
+            if ((flags & 64) && (++it & 7)) { __nanosleep(40); continue; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 w;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(base + (uint32_t)(i * 2048)) : "memory");
+                v.x += w.x; v.y += w.y;
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(i * 2048 + 16384)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+        }
+        if (v.x == 12345.f) cycles[1] = 1;
     } else if (flags & (4 | 8)) {
         const uint32_t lanebase = tb + ((uint32_t)(warp * 32) << 16);
         uint32_t v[8] = {1, 2, 3, 4, 5, 6, 7, 8};
@@ -427,11 +445,9 @@ int main() {
         if (run(5, N, 1, false, reps, &err, &cyc)) return 1;
         printf("T5 SS timing N=%3d: %lld cycles for %d MMAs (M128 K8) = %.1f cycles/MMA\n", N, cyc, reps * 16 * 3, (double)cyc / (reps * 16 * 3));
     }
-    if (rate<32, true, 1>(dcyc, "TS", 0) || rate<32, true, 1>(dcyc, "TS", 1) || rate<32, true, 1>(dcyc, "TS", 2) ||
-        rate<32, true, 1>(dcyc, "TS", 4) || rate<32, true, 1>(dcyc, "TS", 8) || rate<32, true, 1>(dcyc, "TS", 16) ||
-        rate<32, true, 1>(dcyc, "TS", 18) || rate<32, true, 1>(dcyc, "TS", 31) || rate<32, true, 2>(dcyc, "TS", 31) ||
-        rate<16, true, 1>(dcyc, "TS", 16) || rate<64, true, 1>(dcyc, "TS", 16) || rate<128, true, 1>(dcyc, "TS", 16) ||
-        rate<32, false, 1>(dcyc, "SS", 16) || rate<128, false, 1>(dcyc, "SS", 16))
+    if (rate<32, true, 1>(dcyc, "TS", 0) || rate<32, true, 1>(dcyc, "TS", 32) || rate<32, true, 1>(dcyc, "TS", 64) ||
+        rate<32, true, 1>(dcyc, "TS", 16 + 32) || rate<64, true, 1>(dcyc, "TS", 32) || rate<16, true, 1>(dcyc, "TS", 32) ||
+        rate<128, true, 1>(dcyc, "TS", 32) || rate<32, false, 1>(dcyc, "SS", 32))
         return 1;
     return 0;
 }
