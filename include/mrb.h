@@ -167,11 +167,15 @@ int32_t mrb_get_pfb(const mrb_filter *f, int32_t which, void *dst);
  * halo + c*ld_halo; NULL = zeros).  *k0 receives the absolute index of the segment's first output. */
 int32_t mrb_seek(mrb_filter *f, int64_t n0, const void *halo, int64_t ld_halo, int64_t *k0, void *stream);
 
-/* Live tap update (no reference counterpart -- upstream rebuilds the FIRFilter; SURVEY 8f rank 3, host side).
- * Replaces the taps in place: h has the tap dtype and length given at creation, so taps-per-phase, history
- * length, the carried phase state and the per-channel history are all kept.  Banks are rebuilt as mrb_create
- * builds them (src/Filters.jl:21,36,53,73,106-108,138-139); Farrow: poly_coeffs as in mrb_desc (NULL = the
- * library refits).  Synchronises the device. */
+/* Live tap update (no reference counterpart -- upstream rebuilds the FIRFilter and loses its state).
+ * Replaces the taps in place: h has the tap dtype and length given at creation, so taps-per-phase, history length, the
+ * carried phase state and the per-channel history are all kept.  ASYNCHRONOUS and ordered on `stream`, no device-wide
+ * synchronisation: the banks the kernels read from global memory are rebuilt ON THE DEVICE from the raw taps (flipud /
+ * taps2pfb / [diff(h); 0], src/Filters.jl:21,36,53,73,106-108,284-298), the kernels that keep taps in their parameter
+ * block get them with their next launch; work already queued on the stream still filters with the old taps.
+ * Farrow: poly_coeffs as in mrb_desc (NULL = the library refits, mrb_pfb2pnfb).  h may be reused as soon as the call
+ * returns.  mrb_set_taps is the same call on the stream of the handle's last asynchronous call. */
+int32_t mrb_set_taps_async(mrb_filter *f, const void *h, int64_t h_len, const double *poly_coeffs, void *stream);
 int32_t mrb_set_taps(mrb_filter *f, const void *h, int64_t h_len, const double *poly_coeffs);
 
 /* number of CUDA kernels this handle has launched (bench.py's gpu_launches) */

@@ -28,7 +28,7 @@ F32, F64, C64, C128 = 0, 1, 2, 3
 SYMBOLS = ["mrb_create", "mrb_destroy", "mrb_get_info", "mrb_outputlength", "mrb_output_count", "mrb_inputlength",
            "mrb_nextphase", "mrb_taps2pfb", "mrb_pfb2pnfb", "mrb_filt", "mrb_filt_host", "mrb_set_host_pipeline", "mrb_advance", "mrb_reset", "mrb_setphase",
            "mrb_get_state", "mrb_set_state", "mrb_get_history", "mrb_set_history", "mrb_tapsforphase", "mrb_get_pfb",
-           "mrb_seek", "mrb_get_schedule", "mrb_set_taps", "mrb_launch_count", "mrb_set_timing", "mrb_get_timing", "mrb_set_kernel_policy", "mrb_last_kernel", "mrb_last_error", "mrb_version"]
+           "mrb_seek", "mrb_get_schedule", "mrb_set_taps", "mrb_set_taps_async", "mrb_launch_count", "mrb_set_timing", "mrb_get_timing", "mrb_set_kernel_policy", "mrb_last_kernel", "mrb_last_error", "mrb_version"]
 
 
 class Desc(C.Structure):
@@ -99,7 +99,7 @@ def lib():
         "mrb_get_state": (i32, [vp, P(State)]), "mrb_set_state": (i32, [vp, P(State)]),
         "mrb_get_history": (i32, [vp, vp]), "mrb_set_history": (i32, [vp, vp]),
         "mrb_tapsforphase": (i32, [vp, dbl, vp]), "mrb_get_pfb": (i32, [vp, i32, vp]),
-        "mrb_seek": (i32, [vp, i64, vp, i64, P(i64), vp]), "mrb_set_taps": (i32, [vp, vp, i64, vp]), "mrb_get_schedule": (i32, [vp, i64, vp, vp, vp]), "mrb_launch_count": (i32, [vp, P(i64)]),
+        "mrb_seek": (i32, [vp, i64, vp, i64, P(i64), vp]), "mrb_set_taps": (i32, [vp, vp, i64, vp]), "mrb_set_taps_async": (i32, [vp, vp, i64, vp, vp]), "mrb_get_schedule": (i32, [vp, i64, vp, vp, vp]), "mrb_launch_count": (i32, [vp, P(i64)]),
         "mrb_set_kernel_policy": (i32, [vp, i32]),
         "mrb_set_timing": (i32, [vp, i32]), "mrb_get_timing": (i32, [vp, P(dbl), P(i64)]), "mrb_last_kernel": (C.c_char_p, [vp]),
         "mrb_last_error": (C.c_char_p, []), "mrb_version": (C.c_char_p, []),

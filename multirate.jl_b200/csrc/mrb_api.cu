@@ -131,6 +131,7 @@ struct DeviceGuard {                   // the API leaves the caller's current de
 
 struct mrb_filter;
 static void free_device(mrb_filter *f);
+static int32_t order_after_last(mrb_filter *f, cudaStream_t st);
 
 struct mrb_filter {
     int kind, th, tx, ty, device;
@@ -158,6 +159,11 @@ struct mrb_filter {
     cudaStream_t last_stream = nullptr;
     bool last_valid = false;
     cudaEvent_t order_ev = nullptr;
+    // live tap update: pinned + device staging of the raw taps, guarded by an event
+    void *h_taps_stage = nullptr, *d_taps_stage = nullptr;
+    size_t taps_stage_bytes = 0;
+    cudaEvent_t taps_ev = nullptr;
+    bool taps_pending = false;
     // table kinds: the schedule of the call in flight.  The exact replay costs ~0.3 ms per 60 K outputs, and a caller
     // typically asks for the count (to size its buffer) right before it filters: the last replay is cached, keyed by
     // the state it started from and the input length.
@@ -204,6 +210,8 @@ static void free_device(mrb_filter *f) {
     }
     cudaFree(f->d_xs); cudaFree(f->d_ys);
     if (f->order_ev) cudaEventDestroy(f->order_ev);
+    if (f->taps_ev) cudaEventDestroy(f->taps_ev);
+    cudaFreeHost(f->h_taps_stage); cudaFree(f->d_taps_stage);
     tiled_release(f->tiled);
     unit_release(f->unit);
     decim_release(f->decim);
@@ -396,55 +404,116 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
     return MRB_OK;
 }
 
-// Live tap update (host side): replace the taps of a filter in place -- same length and tap dtype,
-// so T, H, the carried phase state and the per-channel history all stay as they are -- e.g. an adaptive filter whose
-// taps change between chunks.  The banks are rebuilt exactly as mrb_create builds them (flipud / taps2pfb /
-// [diff(h);0] / the caller's Farrow fit) and every kernel's copy is refreshed.  Synchronises the device.
-extern "C" int32_t mrb_set_taps(mrb_filter *f, const void *hv, int64_t h_len, const double *poly_coeffs) {
+// Bank construction ON THE DEVICE (src/Filters.jl:21,53 flipud, :284-298 taps2pfb, :106 [diff(h); 0]):
+// from the raw taps h (tap dtype TH) to the phase-major bank rows (compute type R) the kernels read from global memory.
+//   bank[phi*T + (T-1-r)] = h[r*Nphi + phi]   (zero past hLen);   Nphi = 1: bank[i] = h[hLen-1-i]
+//   dbank: the same of dh[i] = h[i+1] - h[i] in TH arithmetic, dh[hLen-1] = 0
+template <typename TH, typename R>
+__global__ void __launch_bounds__(256) k_build_banks(const TH *__restrict__ h, int64_t hLen, int64_t Nphi, int64_t T, R *__restrict__ bank,
+                                                     R *__restrict__ dbank, float *__restrict__ bank_f32) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= Nphi * T) return;
+    const int64_t phi = idx / T, row = idx - phi * T;
+    const int64_t hi = (T - 1 - row) * Nphi + phi;                   // make_bank: rows are filled from the last one up
+    const TH v = hi < hLen ? h[hi] : TH(0);
+    bank[idx] = (R)v;
+    if (bank_f32) bank_f32[idx] = (float)v;
+    if (dbank) {
+        TH d = TH(0);
+        if (hi + 1 < hLen) d = h[hi + 1] - h[hi];                    // [diff(h); 0] in the tap type, :106
+        else if (hi < hLen) d = TH(0);
+        dbank[idx] = (R)d;
+    }
+}
+
+// Live tap update: replace the taps of a filter in place -- same length and tap dtype, so T, H, the
+// carried phase state and the per-channel history all stay as they are -- e.g. an adaptive filter whose taps change
+// between chunks.  ASYNCHRONOUS and ordered on `stream`: no device-wide synchronisation.
+//  * kernels that keep their taps in the kernel PARAMETER block (tiled, unit) are launched with a copy of the host block,
+//    so rewriting the host block is all they need;
+//  * the banks in global memory (d_bank, d_dbank: generic / stream / head / table / tensor-core kernels; the decimator's
+//    residue tables; the Farrow coefficients) are rebuilt ON THE DEVICE by k_build_banks / k_decim_taps from the raw
+//    taps, which travel through a small pinned staging buffer; work already queued on the stream still sees the old banks.
+// Host banks are built into temporaries and committed only when every step succeeded.
+static int32_t set_taps_impl(mrb_filter *f, const void *hv, int64_t h_len, const double *poly_coeffs, cudaStream_t st) {
     if (!f || !hv) return fail(MRB_ERR_BAD_ARGUMENT, "null argument");
     if (h_len != f->hLen) return fail(MRB_ERR_BAD_ARGUMENT, "mrb_set_taps keeps the tap count (%lld), got %lld", (long long)f->hLen, (long long)h_len);
-    std::vector<double> h((size_t)h_len);
+    std::vector<double> h((size_t)h_len), bank, dbank, pnfb;
     for (int64_t i = 0; i < h_len; ++i)
         h[i] = f->th == MRB_F32 ? (double)static_cast<const float *>(hv)[i] : static_cast<const double *>(hv)[i];
     if (f->kind == MRB_STANDARD || f->kind == MRB_DECIMATOR) {
-        for (size_t i = 0; i < h.size(); ++i) f->bank[i] = h[h.size() - 1 - i];            // flipud(h), :21,:53
+        bank.resize(h.size());
+        for (size_t i = 0; i < h.size(); ++i) bank[i] = h[h.size() - 1 - i];               // flipud(h), :21,:53
     } else {
-        make_bank(h, f->Nphi, f->T, f->bank);                                              // taps2pfb, :36,:73,:107,:138
+        make_bank(h, f->Nphi, f->T, bank);                                                 // taps2pfb, :36,:73,:107,:138
     }
     if (f->kind == MRB_ARBITRARY) {
         std::vector<double> dh(h.size(), 0.0);                                             // :106
         for (size_t i = 0; i + 1 < h.size(); ++i)
             dh[i] = f->th == MRB_F32 ? (double)((float)h[i + 1] - (float)h[i]) : h[i + 1] - h[i];
-        make_bank(dh, f->Nphi, f->T, f->dbank);
+        make_bank(dh, f->Nphi, f->T, dbank);
     }
     if (f->kind == MRB_FARROW) {
-        if (poly_coeffs) f->pnfb.assign(poly_coeffs, poly_coeffs + f->T * (f->polyorder + 1));
-        else fit_pnfb(f->bank, f->Nphi, f->T, f->polyorder, f->th == MRB_F32, f->pnfb.data());
+        pnfb.resize(f->pnfb.size());
+        if (poly_coeffs) pnfb.assign(poly_coeffs, poly_coeffs + f->T * (f->polyorder + 1));
+        else fit_pnfb(bank, f->Nphi, f->T, f->polyorder, f->th == MRB_F32, pnfb.data());
     }
-    if (f->device < 0) return MRB_OK;
-
-    DeviceGuard guard(f->device);
-    CU(cudaDeviceSynchronize());                       // kernels in flight still read the old banks
-    const bool dbl = is_double(f->ty);
-    auto refresh = [&](const std::vector<double> &src, void *dst) -> cudaError_t {
-        if (dbl) return cudaMemcpy(dst, src.data(), src.size() * sizeof(double), cudaMemcpyHostToDevice);
-        std::vector<float> tmp(src.begin(), src.end());
-        return cudaMemcpy(dst, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice);
-    };
-    CU(refresh(f->bank, f->d_bank));
-    if (f->kind == MRB_ARBITRARY) CU(refresh(f->dbank, f->d_dbank));
-    if (f->kind == MRB_FARROW) CU(cudaMemcpy(f->d_pnfb, f->pnfb.data(), f->pnfb.size() * sizeof(double), cudaMemcpyHostToDevice));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, f->device));
-    tiled_release(f->tiled); unit_release(f->unit); decim_release(f->decim);
-    int32_t rc = tiled_prepare(f->tiled, f->kind, f->tx, f->ty, f->L, f->M, f->Nphi, f->T, f->bank, f->dbank, prop);
-    if (rc != 0) return fail(MRB_ERR_CUDA, "tiled_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
-    rc = unit_prepare(f->unit, f->kind, f->tx, f->ty, f->L, f->M, f->T, f->bank, prop);
-    if (rc != 0) return fail(MRB_ERR_CUDA, "unit_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
-    rc = decim_prepare(f->decim, f->kind, f->tx, f->ty, f->L, f->M, f->T, f->bank, prop);
-    if (rc != 0) return fail(MRB_ERR_CUDA, "decim_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
-    CU(cudaDeviceSynchronize());
+    if (f->device >= 0) {
+        DeviceGuard guard(f->device);
+        int32_t rc = order_after_last(f, st);
+        if (rc) return rc;
+        const size_t hb = (size_t)h_len * (f->th == MRB_F32 ? 4 : 8), pb = pnfb.size() * sizeof(double);
+        if (f->taps_stage_bytes < hb + pb) {
+            if (f->taps_pending) { CU(cudaEventSynchronize(f->taps_ev)); f->taps_pending = false; }
+            cudaFreeHost(f->h_taps_stage); cudaFree(f->d_taps_stage);
+            f->h_taps_stage = nullptr; f->d_taps_stage = nullptr; f->taps_stage_bytes = 0;
+            CU(cudaMallocHost(&f->h_taps_stage, hb + pb + 64));
+            CU(cudaMalloc(&f->d_taps_stage, hb + 64));
+            f->taps_stage_bytes = hb + pb;
+            if (!f->taps_ev) CU(cudaEventCreateWithFlags(&f->taps_ev, cudaEventDisableTiming));
+        }
+        if (f->taps_pending) { CU(cudaEventSynchronize(f->taps_ev)); f->taps_pending = false; }   // the last update's copies have left the staging buffer
+        memcpy(f->h_taps_stage, hv, hb);
+        CU(cudaMemcpyAsync(f->d_taps_stage, f->h_taps_stage, hb, cudaMemcpyHostToDevice, st));
+        if (pb) {
+            memcpy(static_cast<char *>(f->h_taps_stage) + hb, pnfb.data(), pb);
+            CU(cudaMemcpyAsync(f->d_pnfb, static_cast<char *>(f->h_taps_stage) + hb, pb, cudaMemcpyHostToDevice, st));
+        }
+        CU(cudaEventRecord(f->taps_ev, st));
+        f->taps_pending = true;
+        const bool dbl = is_double(f->ty);
+        const int64_t nb = f->Nphi * f->T;
+        const unsigned g = (unsigned)ceil_div(nb, 256);
+        float *bank_f32 = nullptr;                                     // the decimator tables are built from float32 rows
+        if (f->decim.ok && !dbl) bank_f32 = static_cast<float *>(f->d_bank);
+        if (f->th == MRB_F32) {
+            if (dbl) k_build_banks<float, double><<<g, 256, 0, st>>>((const float *)f->d_taps_stage, h_len, f->Nphi, f->T, (double *)f->d_bank, (double *)f->d_dbank, nullptr);
+            else k_build_banks<float, float><<<g, 256, 0, st>>>((const float *)f->d_taps_stage, h_len, f->Nphi, f->T, (float *)f->d_bank, (float *)f->d_dbank, nullptr);
+        } else {
+            if (dbl) k_build_banks<double, double><<<g, 256, 0, st>>>((const double *)f->d_taps_stage, h_len, f->Nphi, f->T, (double *)f->d_bank, (double *)f->d_dbank, nullptr);
+            else k_build_banks<double, float><<<g, 256, 0, st>>>((const double *)f->d_taps_stage, h_len, f->Nphi, f->T, (float *)f->d_bank, (float *)f->d_dbank, nullptr);
+        }
+        ++f->launches;
+        if (bank_f32) { decim_set_taps(f->decim, bank_f32, st); ++f->launches; }
+        CU(cudaGetLastError());
+        // parameter-block kernels: their host blocks (copied into every launch)
+        tiled_set_bank(f->tiled, f->L, f->T, bank);
+        unit_set_bank(f->unit, f->T, bank);
+        f->last_stream = st; f->last_valid = true;
+    }
+    f->bank.swap(bank);
+    if (f->kind == MRB_ARBITRARY) f->dbank.swap(dbank);
+    if (f->kind == MRB_FARROW) f->pnfb.swap(pnfb);
     return MRB_OK;
+}
+
+extern "C" int32_t mrb_set_taps_async(mrb_filter *f, const void *hv, int64_t h_len, const double *poly_coeffs, void *stream) {
+    return set_taps_impl(f, hv, h_len, poly_coeffs, (cudaStream_t)stream);
+}
+
+// The same on the stream of the handle's last asynchronous call (the default stream before any)
+extern "C" int32_t mrb_set_taps(mrb_filter *f, const void *hv, int64_t h_len, const double *poly_coeffs) {
+    return set_taps_impl(f, hv, h_len, poly_coeffs, f && f->last_valid ? f->last_stream : (cudaStream_t) nullptr);
 }
 
 extern "C" int32_t mrb_destroy(mrb_filter *f) {

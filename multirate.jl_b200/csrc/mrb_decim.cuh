@@ -286,6 +286,29 @@ static inline int32_t decim_prepare(DecPlan &p, int kind, int tx, int ty, int64_
     return 0;
 }
 
+// Live tap update on the device: the per-alignment residue tables from the flipped taps (bank[i] = hflip[i], float32),
+// one thread per (alignment, tap).  Same layout as decim_prepare builds on the host.
+__global__ void __launch_bounds__(256) k_decim_taps(const float *__restrict__ bank, int T, int M, int A, float *__restrict__ taps) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int total = A * kDecTQ * 32;
+    if (idx >= total) return;
+    // zero everything first: a slot (delta, j, q) holds padded tap ip = j*M + q, i.e. bank[ip - zf] when inside [0, T)
+    const int delta = idx / (kDecTQ * 32), rem = idx - delta * kDecTQ * 32, j = rem / 32, q = rem & 31;
+    float v = 0.f;
+    if (q < M) {
+        const int zf = kDecTQ * M - T - delta;
+        const int i = j * M + q - zf;
+        if (i >= 0 && i < T) v = bank[i];
+    }
+    taps[idx] = v;
+}
+
+static inline void decim_set_taps(DecPlan &p, const float *d_bank_f32, cudaStream_t st) {
+    if (!p.ok) return;
+    const int A = p.cplx ? 2 : 4;
+    k_decim_taps<<<(A * kDecTQ * 32 + 255) / 256, 256, 0, st>>>(d_bank_f32, (int)p.T, p.M, A, p.d_taps);
+}
+
 // Launch for outputs [k_begin, N) of this chunk.  Returns k_begin (>= 0; the caller computes the outputs before it
 // with the generic kernel), -1 when the call is not covered, -2 on a CUDA error.
 static inline int64_t decim_try_launch(DecPlan &p, const GenParams &G, cudaStream_t st, const char **name,

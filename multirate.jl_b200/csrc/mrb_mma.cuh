@@ -18,7 +18,8 @@
 //    MMAs read only B from shared memory (TS mode: SS mode would re-read the 128-row A tile for every instruction);
 //  * B (the tap tiles, already split and stored as the K-major SWIZZLE_128B shared-memory image) is built once per
 //    chunk for all channels by a pre-pass (k_mma_tiles) and streamed by bulk copies;
-//  * warp-specialised, no CTA-wide barrier in the loop: x loader, tile loader, two MMA issuers (one elected lane each),
+//  * warp-specialised, no CTA-wide barrier in the loop: x loader, tile loader, MMA issuer (one elected lane) with a look-ahead
+//    warp that does its mbarrier waits one group ahead,
 //    4 converter warps, 4 epilogue warps (tcgen05.ld -> swizzled staging -> TMA store), all coupled by mbarriers;
 //    tcgen05.commit releases tile slots, ring columns and hands accumulators to the epilogue.
 // Outputs whose window reaches into the history are computed by k_generic, as for every fast path.
@@ -36,7 +37,7 @@ constexpr int kMmaNXB = 4;              // x boxes in flight in shared memory
 constexpr int kMmaNAB = 7;              // boxes the tensor-memory rings hold (RC = 224 columns each)
 constexpr int kMmaRC = kMmaNAB * kMmaBox;
 constexpr int kMmaMaxKB = 6;            // K <= 192: the MMAs of a group read at most 7 boxes
-constexpr int kMmaThreads = 384;        // warps 0-3 epilogue, 4-7 converters, 8 x loader, 9 tile loader, 10-11 MMA issuers
+constexpr int kMmaThreads = 384;        // warps 0-3 epilogue, 4-7 converters, 8 x loader, 9 tile loader, 10 MMA issuer, 11 its look-ahead waiter
 constexpr int kMmaMaxGT = 512;          // groups per time tile (their window starts are staged in shared memory)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -187,6 +188,7 @@ struct alignas(16) MmaParams {
     int KS;                    // K-steps (8 samples) actually issued per group (<= 4 KB)
     int NWB;                   // tile slots in shared memory
     int tile_bytes;            // 2 * KB * G * 128
+    int nissue;                // 2: a look-ahead warp does the issuer's waits (default); 1: the issuer waits itself (MRB_MMA_ISSUERS=1)
     int period;                // tile of group g = tile (g mod period): g_end - 0 for aperiodic tables
     int resident;              // period <= NWB: every tile is loaded once and stays in its slot
     int nch;                   // channels (rows past it read zero history)
@@ -271,14 +273,16 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
     auto B_DFULL = [&](int i) { return bar0 + 8u * (uint32_t)(32 + i); };          // 2
     auto B_DEMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(34 + i); };
     const uint32_t B_GS = bar0 + 8u * 36u;
+    auto B_GO = [&](int i) { return bar0 + 8u * (uint32_t)(42 + i); };             // 4 (slot 40 holds the tensor-memory base)
 
     if (tid == 0) {
         if (smem_u32(smem) & 1023u) __trap();
         for (int i = 0; i < NXB; ++i) { mbar_init(B_XFULL(i), 1); mbar_init(B_XEMPTY(i), 128); }
-        for (int i = 0; i < NAB; ++i) { mbar_init(B_AFULL(i), 128); mbar_init(B_AEMPTY(i), 2); }
+        for (int i = 0; i < NAB; ++i) { mbar_init(B_AFULL(i), 128); mbar_init(B_AEMPTY(i), 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(B_WFULL(i), 1); mbar_init(B_WEMPTY(i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(B_DFULL(i), 1); mbar_init(B_DEMPTY(i), 128); }
         mbar_init(B_GS, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(B_GO(i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmy) : "memory");
@@ -342,49 +346,64 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
             }
             if (prof) pr[1] = c0;
         }
-    } else if (warp >= 10) {
-        // ---------------- MMA issuers: TWO warps, issuer i takes the groups w = i, i+2, ... (accumulator buffer i).  While
-        // one issuer is blocked on the full tensor-pipe queue, the other does the waits of the next group (every mbarrier
-        // try_wait costs ~90 cycles even when it succeeds, plus fence, descriptors, commits: ~700 cycles per group that a
-        // single issuer left the pipe idle -- 41 % tensor-pipe activity, ncu profiles/r2_ncu_mma_*).  The pipe
-        // interleaves the MMAs of the two groups; they use different accumulators and tiles.
-        const int iss = warp - 10;
+    } else if (warp == 11) {
+        // ---------------- look-ahead waiter.  Everything group w must wait for -- its window converted (a_full), its tile
+        // landed (w_full), its accumulator buffer drained (d_empty) -- is waited for HERE, one group ahead of the issuer,
+        // and folded into one mbarrier GO[w & 3].  Every try_wait costs ~90 cycles even when it succeeds at once; with the
+        // issuer doing the three or four of them itself, plus fence and commits, the tensor pipe sat idle ~700 cycles per
+        // group (41 % tensor-pipe activity, profiles/r2_ncu_mma_c3b).  (Two issuer warps alternating groups hid the same
+        // latency and measured +23 %, but faulted about once in 1000 launches: MMAs are issued by ONE thread only.)
+        if (P.nissue == 2) {
+            int boxes_ready = 0, ar_slot = 0;
+            uint32_t ar_par = 0, w_par = 0;
+            const int ws_wrap = P.resident ? P.period : P.NWB;
+            int ws = P.resident ? (int)(g0 % P.period) : 0;
+            for (int w = 0; w < ng; ++w) {
+                const int need = (gs[w] - xbase + P.KS * 8 - 1) / kMmaBox;
+                for (; boxes_ready <= need; ++boxes_ready) {
+                    mbar_wait(B_AFULL(ar_slot), ar_par);
+                    if (++ar_slot == NAB) { ar_slot = 0; ar_par ^= 1u; }
+                }
+                mbar_wait(B_WFULL(ws), w_par);
+                // (d_empty of group w also proves that the issuer has consumed GO of group w - 2, hence of w - 4: the
+                // four GO barriers are never lapped)
+                if (w >= 2) mbar_wait(B_DEMPTY(w & 1), (uint32_t)(((w >> 1) - 1) & 1));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(B_GO(w & 3));
+                if (++ws == ws_wrap) { ws = 0; if (!P.resident) w_par ^= 1u; }
+            }
+        }
+    } else if (warp == 10) {
+        // ---------------- MMA issuer (one elected lane)
+        const bool ahead = P.nissue == 2;                              // the waits are done by the look-ahead warp
         const uint32_t idesc = umma_idesc_tf32(kMmaRows, G);
         const uint32_t lo_off = (uint32_t)(P.KB * G * 128) >> 4;       // hi -> lo half of a tile, in descriptor units
         int boxes_ready = 0, dead = 0;
         int ar_slot = 0;                                               // a_full slot of box `boxes_ready` and its phase parity
         uint32_t ar_par = 0;
         const int ws_wrap = P.resident ? P.period : P.NWB;
-        int ws = P.resident ? (int)((g0 + iss) % P.period) : iss % P.NWB;   // tile slot of group w and its parity, kept without divisions
-        uint32_t w_par = P.resident ? 0u : (uint32_t)((iss / P.NWB) & 1);
+        int ws = P.resident ? (int)(g0 % P.period) : 0;                 // tile slot of group w and its parity, kept without divisions
+        uint32_t w_par = 0;
         long long c4 = 0;
-        for (int w = iss; w < ng; w += 2) {
+        for (int w = 0; w < ng; ++w) {
             const int a0 = gs[w] - xbase;                              // multiple of 8
             const int need = (a0 + P.KS * 8 - 1) / kMmaBox;
-            // boxes this issuer never reads again: everything before the first box of ITS next group
-            const int next_first = w + 2 < ng ? (gs[w + 2] - xbase) / kMmaBox : jlast + 1;
-            // (boxes before this group's first one are released BEFORE waiting for its window: issuer 1 reads none of the
-            // boxes before its first group, and the converters need its release to refill them -- without this the two
-            // wait for each other as soon as group 1's window reaches box NAB)
-            for (const int first = a0 / kMmaBox; dead < first; ++dead) {
-                if (boxes_ready <= dead) {
+            // ring boxes no later group reads: everything before the next group's first box
+            const int next_first = w + 1 < ng ? (gs[w + 1] - xbase) / kMmaBox : jlast + 1;
+            if (ahead) {
+                mbar_wait_prof(B_GO(w & 3), (uint32_t)((w >> 2) & 1), prof, c0);
+            } else {
+                for (; boxes_ready <= need; ++boxes_ready) {
                     mbar_wait_prof(B_AFULL(ar_slot), ar_par, prof, c0);
                     if (++ar_slot == NAB) { ar_slot = 0; ar_par ^= 1u; }
-                    ++boxes_ready;
                 }
-                if (elect_one()) tc_commit(B_AEMPTY(dead % NAB));
-                __syncwarp();
+                mbar_wait_prof(B_WFULL(ws), w_par, prof, c1);
+                if (w >= 2) mbar_wait_prof(B_DEMPTY(w & 1), (uint32_t)(((w >> 1) - 1) & 1), prof, c2);
             }
-            for (; boxes_ready <= need; ++boxes_ready) {
-                mbar_wait_prof(B_AFULL(ar_slot), ar_par, prof, c0);
-                if (++ar_slot == NAB) { ar_slot = 0; ar_par ^= 1u; }
-            }
-            mbar_wait_prof(B_WFULL(ws), w_par, prof, c1);
-            if (w >= 2) mbar_wait_prof(B_DEMPTY(iss), (uint32_t)(((w >> 1) - 1) & 1), prof, c2);
             const long long tf0 = prof ? clock64() : 0;
             tc_fence_after();
             if (prof) c4 += clock64() - tf0;
-            const uint32_t d = tb + (uint32_t)(C::TM_D + iss * G);
+            const uint32_t d = tb + (uint32_t)(C::TM_D + (w & 1) * G);
             const uint64_t bh0 = umma_desc_sw128(smem_u32(wring) + (uint32_t)(ws * P.tile_bytes));
             const int col0 = a0 % kMmaRC;
             const long long ti0 = prof ? clock64() : 0;
@@ -417,35 +436,15 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
                 default: mma_issue_group<G, 24>(d, ah, al, col0, bh0, lo_off, idesc); break;
                 }
                 tc_commit(B_WEMPTY(ws));                               // the tile slot may be refilled
-                tc_commit(B_DFULL(iss));                               // the accumulators are complete
+                tc_commit(B_DFULL(w & 1));                             // the accumulators are complete
+                for (int b = dead; b < next_first; ++b) tc_commit(B_AEMPTY(b % NAB));   // ring boxes nobody reads any more
             }
             __syncwarp();
             if (prof) c3 += clock64() - ti0;
-            // A ring box is free once BOTH issuers have passed it (a_empty counts two arrivals).  An issuer observes a
-            // box's a_full phase before it releases the box -- also boxes it skips (steep decimation) -- so the
-            // converters can never complete a slot's next phase behind its back.
-            for (; dead < next_first; ++dead) {
-                if (boxes_ready <= dead) {
-                    mbar_wait_prof(B_AFULL(ar_slot), ar_par, prof, c0);
-                    if (++ar_slot == NAB) { ar_slot = 0; ar_par ^= 1u; }
-                    ++boxes_ready;
-                }
-                if (elect_one()) tc_commit(B_AEMPTY(dead % NAB));
-                __syncwarp();
-            }
-            for (int q = 0; q < 2; ++q)                                // two groups on
-                if (++ws == ws_wrap) { ws = 0; if (!P.resident) w_par ^= 1u; }   // resident tiles: phase 0 stays complete
+            if (next_first > dead) dead = next_first;
+            if (++ws == ws_wrap) { ws = 0; if (!P.resident) w_par ^= 1u; }   // resident tiles: phase 0 stays complete
         }
-        for (; dead <= jlast; ++dead) {                                // (an issuer without groups still releases every box)
-            if (boxes_ready <= dead) {
-                mbar_wait(B_AFULL(ar_slot), ar_par);
-                if (++ar_slot == NAB) { ar_slot = 0; ar_par ^= 1u; }
-                ++boxes_ready;
-            }
-            if (elect_one()) tc_commit(B_AEMPTY(dead % NAB));
-            __syncwarp();
-        }
-        if (prof && lane == 0 && iss == 0) { pr[15] = c4; pr[2] = c0; pr[3] = c1; pr[4] = c2; pr[11] = c3; pr[14] = clock64() - t_start; }
+        if (prof && lane == 0) { pr[15] = c4; pr[2] = c0; pr[3] = c1; pr[4] = c2; pr[11] = c3; pr[14] = clock64() - t_start; }
     } else if (warp >= 4) {
         // ---------------- converters: thread = channel = tensor-memory lane; box j -> columns (j mod NAB) * 32 of both rings
         const int q = warp - 4;                                        // lane quadrant (warp index mod 4)
@@ -646,6 +645,8 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     P.prof = want_prof ? d_prof : nullptr;
     P.g_begin = g_begin; P.g_end = groups; P.y0 = y0; P.KB = KB; P.KS = KS; P.NWB = nwb; P.tile_bytes = tile_bytes;
     P.period = (int)ntiles; P.resident = resident ? 1 : 0;
+    static const int n_issuers = getenv("MRB_MMA_ISSUERS") && atoi(getenv("MRB_MMA_ISSUERS")) == 1 ? 1 : 2;
+    P.nissue = n_issuers;
     P.nch = (int)G.nch; P.hist = static_cast<const float *>(G.hist); P.H = G.H;
     const int64_t span = groups - g_begin;
     const int64_t cgroups = ceil_div(G.nch, kMmaRows);
@@ -689,10 +690,19 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
         k_mma_tiles<GG><<<gb, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, KB, S, G.H,
                                             S.mode == 2 ? nrows : cnt, nrows, groups, rw.d_tiles, rw.d_gstart);
         ++*launches;
+        if (trace && cudaPeekAtLastError() != cudaSuccess)
+            fprintf(stderr, "[mrb] k_mma_tiles failed: %s (mode %d cnt %lld groups %lld ntiles %lld KB %d)\n", cudaGetErrorString(cudaPeekAtLastError()),
+                    S.mode, (long long)cnt, (long long)groups, (long long)ntiles, KB);
     }
     dim3 grid((unsigned)cgroups, (unsigned)tiles);
     k_mma_fir<GG><<<grid, kMmaThreads, fixed + nwb * tile_bytes, st>>>(tmx, tmy, rw.d_tiles, rw.d_gstart, P);
-    if (cudaPeekAtLastError() != cudaSuccess) return -2;
+    if (cudaPeekAtLastError() != cudaSuccess) {
+        if (trace)
+            fprintf(stderr, "[mrb] k_mma_fir failed: %s (mode %d cnt %lld y0 %lld n_in %lld nch %lld groups %lld tiles %lld GT %d KB %d KS %d NWB %d period %d resident %d span %lld H %lld)\n",
+                    cudaGetErrorString(cudaPeekAtLastError()), S.mode, (long long)cnt, (long long)y0, (long long)G.n_in, (long long)G.nch, (long long)groups,
+                    (long long)tiles, P.GT, KB, KS, nwb, P.period, P.resident, (long long)max_group_span, (long long)G.H);
+        return -2;
+    }
     if (want_prof && (int64_t)cgroups * tiles <= 4096) {
         static int shown = 0;
         if (shown++ < 3) {

@@ -438,6 +438,16 @@ static inline int32_t tiled_prepare(TiledPlan &p, int kind, int tx, int ty, int6
     return 0;
 }
 
+// Live tap update: rewrite the run-ordered bank of an existing plan (host parameter block; the next launch carries it).
+static inline void tiled_set_bank(TiledPlan &p, int64_t L, int64_t T, const std::vector<double> &bank) {
+    if (!p.ok) return;
+    float *hb = reinterpret_cast<float *>(p.hp->bank);
+    for (int64_t j = 0; j < L + kRMAX - 1; ++j) {
+        const int64_t ph = ((j % L) * (int64_t)p.hp->M) % L;            // the branch run-order row j holds (tiled_prepare)
+        for (int64_t i = 0; i < T; ++i) hb[j * kTPAD + (kTPAD - T) + i] = (float)bank[ph * T + i];
+    }
+}
+
 // Launch the tiled kernel for outputs [k_begin, N) of this chunk.  Returns k_begin (>= 0; the caller computes
 // [0, k_begin) with the generic kernel), -1 when the call is not covered, -2 on a CUDA error.
 static inline int64_t tiled_try_launch(TiledPlan &p, const GenParams &G, cudaStream_t st, const char **name,

@@ -429,6 +429,20 @@ static inline int32_t unit_prepare(UnitPlan &p, int kind, int tx, int ty, int64_
     return 0;
 }
 
+// Live tap update: rewrite the padded bank of an existing plan (host parameter block; the next launch carries it).
+static inline void unit_set_bank(UnitPlan &p, int64_t T, const std::vector<double> &bank) {
+    if (!p.ok) return;
+    if (p.cplx) {
+        const int64_t Tpc = (int64_t)p.nblk * kUnitCTB;
+        for (int64_t ph = 0; ph < p.L; ++ph)
+            for (int64_t i = 0; i < T; ++i) p.hpc->bank[ph * Tpc + (Tpc - T) + i] = (float)bank[ph * T + i];
+    } else {
+        const int64_t Tp = (int64_t)p.nblk * kUnitTB;
+        for (int64_t ph = 0; ph < p.L; ++ph)
+            for (int64_t i = 0; i < T; ++i) p.hp->bank[ph * Tp + (Tp - T) + i] = (float)bank[ph * T + i];
+    }
+}
+
 // Launch for inputs [n_begin, n_in) of this chunk.  Returns the first OUTPUT the kernel covers (>= 0; the caller
 // computes the outputs before it with the generic kernel), -1 when the call is not covered, -2 on a CUDA error.
 static inline int64_t unit_try_launch(UnitPlan &p, const GenParams &G, cudaStream_t st, const char **name,

@@ -490,9 +490,11 @@ class FIRFilter:
         self._pending_state = None
         return self
 
-    def set_taps(self, h):
+    def set_taps(self, h, stream=None):
         """Replace the taps in place (same length and dtype), keeping phase state and history -- an adaptive filter whose
-        taps change between chunks (upstream would rebuild the FIRFilter and lose its state)."""
+        taps change between chunks (upstream would rebuild the FIRFilter and lose its state).
+        Asynchronous: ordered on `stream` (a cudaStream_t value; default: torch's current stream when torch is loaded,
+        else the stream of the handle's last call), no device synchronisation; banks are rebuilt on the device."""
         h = np.ascontiguousarray(h, dtype=self._h.dtype)
         if h.shape != self._h.shape:
             raise ValueError("set_taps keeps the tap count (%d)" % len(self._h))
@@ -500,8 +502,16 @@ class FIRFilter:
         if self._kind == _ffi.FARROW:
             self._pnfb = np.ascontiguousarray(pfb2pnfb(taps2pfb(h, self._n_phi), self._polyorder))
         if self._handle is not None:
-            _ffi.check(_ffi.lib().mrb_set_taps(self._handle, h.ctypes.data, len(h),
-                                               self._pnfb.ctypes.data if self._pnfb is not None else None))
+            pn = self._pnfb.ctypes.data if self._pnfb is not None else None
+            if stream is None and not getattr(self, "_host_only", False):
+                import sys
+                torch = sys.modules.get("torch")
+                if torch is not None and torch.cuda.is_available():
+                    stream = torch.cuda.current_stream(self._device).cuda_stream
+            if stream is None:
+                _ffi.check(_ffi.lib().mrb_set_taps(self._handle, h.ctypes.data, len(h), pn))
+            else:
+                _ffi.check(_ffi.lib().mrb_set_taps_async(self._handle, h.ctypes.data, len(h), pn, stream))
         return self
 
     def seek(self, n0, halo=None):
