@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -372,8 +373,20 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
         CU(cudaGetDeviceCount(&ndev));
         if (f->device >= ndev) return fail(MRB_ERR_NO_DEVICE, "device %d not present (%d devices)", f->device, ndev);
         DeviceGuard guard(f->device);
+        // cudaGetDeviceProperties costs milliseconds: the one-shot filt(h, x, ratio) creates a handle per call, so the
+        // properties are looked up once per device and process
+        static std::mutex prop_mu;
+        static std::vector<std::pair<int, cudaDeviceProp>> prop_cache;
         cudaDeviceProp prop;
-        CU(cudaGetDeviceProperties(&prop, f->device));
+        {
+            std::lock_guard<std::mutex> lk(prop_mu);
+            bool hit = false;
+            for (auto &e : prop_cache) if (e.first == f->device) { prop = e.second; hit = true; break; }
+            if (!hit) {
+                CU(cudaGetDeviceProperties(&prop, f->device));
+                prop_cache.emplace_back(f->device, prop);
+            }
+        }
         if (prop.major != 10)
             return fail(MRB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library holds sm_100a code only", f->device,
                         prop.major, prop.minor);
@@ -1165,16 +1178,25 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
         const int64_t nc = std::min(cb, f->nch - c0);
         char *dx = static_cast<char *>(f->d_xs) + b * xb, *dy = static_cast<char *>(f->d_ys) + b * yb;
         cudaStream_t st = sts[b];
-        if (n_in > 0)
-            CU(cudaMemcpy2DAsync(dx, (size_t)lxs * es, static_cast<const char *>(x) + (size_t)(c0 * ldx) * es,
-                                 (size_t)ldx * es, (size_t)n_in * es, (size_t)nc, cudaMemcpyHostToDevice, st));
+        // (contiguous rows on both sides -- the usual case -- go as ONE 1-D copy: the DMA engines do fewer, longer bursts)
+        if (n_in > 0) {
+            if (ldx == n_in && lxs == n_in)
+                CU(cudaMemcpyAsync(dx, static_cast<const char *>(x) + (size_t)(c0 * ldx) * es, (size_t)nc * (size_t)n_in * es, cudaMemcpyHostToDevice, st));
+            else
+                CU(cudaMemcpy2DAsync(dx, (size_t)lxs * es, static_cast<const char *>(x) + (size_t)(c0 * ldx) * es,
+                                     (size_t)ldx * es, (size_t)n_in * es, (size_t)nc, cudaMemcpyHostToDevice, st));
+        }
         // arbitrary / farrow: every block uploads the schedule slices and builds the tap rows it needs into the table
         // context of ITS stream (TableCtx): blocks in flight on other streams never see these buffers change
         rc = run_channels(f, dx, lxs, n_in, dy, lys, N, c0, nc, st, b);
         if (rc) return rc;
-        if (N > 0)
-            CU(cudaMemcpy2DAsync(static_cast<char *>(y) + (size_t)(c0 * ldy) * eo, (size_t)ldy * eo, dy, (size_t)lys * eo,
-                                 (size_t)N * eo, (size_t)nc, cudaMemcpyDeviceToHost, st));
+        if (N > 0) {
+            if (ldy == N && lys == N)                      // contiguous on both sides (only the N valid samples of a row are ever written)
+                CU(cudaMemcpyAsync(static_cast<char *>(y) + (size_t)(c0 * ldy) * eo, dy, (size_t)nc * (size_t)N * eo, cudaMemcpyDeviceToHost, st));
+            else
+                CU(cudaMemcpy2DAsync(static_cast<char *>(y) + (size_t)(c0 * ldy) * eo, (size_t)ldy * eo, dy, (size_t)lys * eo,
+                                     (size_t)N * eo, (size_t)nc, cudaMemcpyDeviceToHost, st));
+        }
     }
     for (int i = 0; i < nst; ++i) CU(cudaStreamSynchronize(sts[i]));
     f->last_valid = false;                                 // nothing of this handle is in flight any more

@@ -613,6 +613,9 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     if (((uintptr_t)G.x & 15) || ((uintptr_t)G.y & 15) || (G.ldx % 4) || (G.ldy % 4)) MRB_MMA_SKIP("alignment");
     if (G.n_in >= (1ll << 31) - 4096 || y0 + cnt >= (1ll << 31) - 4096) MRB_MMA_SKIP("size");
     if (y0 % GG) MRB_MMA_SKIP("slice start");
+    // a CTA is 128 channels wide (UMMA M): with a handful of channels the other kernels win (README benchmark, ONE channel:
+    // k_stream 0.024 ms, this kernel 0.19 ms)
+    if (G.nch < 48) MRB_MMA_SKIP("too few channels for a 128-row tile");
     const int64_t kneed = p.T + 7 + max_group_span;                   // samples a group's window spans at worst
     const int KB = (int)ceil_div(kneed, 32);
     if (KB > kMmaMaxKB) MRB_MMA_SKIP("window group wider than the tensor-memory ring");
