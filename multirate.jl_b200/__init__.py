@@ -8,7 +8,7 @@ The directory name contains a dot, so import it through the repo-root shim:
 """
 from . import _ffi
 from ._ffi import MrbError, build
-from .sharding import channel_shard, filt_long_stream, segment_bounds, segment_plan
+from .sharding import LongStream, channel_shard, filt_long_stream, segment_bounds, segment_plan
 from .firdesign import (BANDPASS, BANDSTOP, HIGHPASS, LOWPASS, FIRResponse, blackman, firdes, firprototype, hamming, hanning,
                         kaiser, kaiserlength)
 from .filters import (FIRArbitrary, FIRDecimator, FIRFarrow, FIRFilter, FIRInterpolator, FIRKernel, FIRRational,
@@ -17,6 +17,6 @@ from .filters import (FIRArbitrary, FIRDecimator, FIRFarrow, FIRFilter, FIRInter
 
 __all__ = ["FIRFilter", "FIRKernel", "FIRStandard", "FIRInterpolator", "FIRDecimator", "FIRRational", "FIRArbitrary",
            "FIRFarrow", "filt", "filt_", "reset", "setphase", "outputlength", "inputlength", "taps2pfb", "tapsforphase",
-           "tapsforphase_", "nextphase", "polyfit", "pfb2pnfb", "MrbError", "build", "channel_shard", "segment_bounds", "segment_plan", "filt_long_stream",
+           "tapsforphase_", "nextphase", "polyfit", "pfb2pnfb", "MrbError", "build", "channel_shard", "segment_bounds", "segment_plan", "filt_long_stream", "LongStream",
            "firdes", "firprototype", "kaiserlength", "FIRResponse", "LOWPASS", "BANDPASS", "HIGHPASS", "BANDSTOP", "kaiser",
            "hanning", "hamming", "blackman"]

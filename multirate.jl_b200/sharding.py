@@ -42,66 +42,84 @@ def segment_plan(filt, n_samples: int, world: int, align: int = 1):
     return plan
 
 
+class LongStream:
+    """One very long single-channel stream at multichannel speed, with no copy and no collective (BASELINE
+    configs[4] "one 2^31-sample stream split into segments with tap-length halo").
+
+    The stream (or one rank's M-aligned segment of it) is viewed in place as a channel-major matrix of `rows` sub-segments
+    of `seg` samples, seg a multiple of the decimation M: every sub-segment then starts from the constructor state (phase 0,
+    deficit 1; src/Filters.jl:567-571 in closed form), its history is simply the H samples that precede it in memory (the
+    halo), and it produces exactly seg*L/M outputs, so the output matrix is the output stream, in place.  The tail that
+    does not fill a sub-segment runs through a one-channel filter seeked to its position.
+
+    The plan and the two handles are built once for a stream length `n` and sample dtype; `run(x, halo0)` then filters any
+    stream of that length (e.g. successive blocks of a recording, or the same block on every step of a benchmark):
+    `halo0` = the H samples that precede x[0] (None at the start of the stream).  Across GPUs every rank builds one for its
+    own segment (`segment_bounds(..., align=M)`); nothing but the halo crosses between ranks."""
+
+    def __init__(self, h, ratio, n, dtype, device=0, rows_target: int = 8192):
+        import math
+        from fractions import Fraction
+
+        import numpy as np
+
+        from .filters import FIRFilter
+        self.h, self.ratio = h, Fraction(ratio)
+        L, M = self.ratio.numerator, self.ratio.denominator
+        self.n, self.tx = int(n), np.dtype(dtype)
+        probe = FIRFilter(h, self.ratio, nchannels=1, sample_dtype=self.tx, device=-1)
+        self.H = probe.historyLen
+        # sub-segment length: a multiple of M whose input and output row pitches are multiples of 16 bytes
+        al = max(1, 16 // self.tx.itemsize)
+        unit = M * al // math.gcd(M, al)
+        while (unit * L // M) % al:
+            unit *= 2
+        self.seg = max(unit, -(-(-(-self.n // max(rows_target, 1))) // unit) * unit)     # ceil: at most rows_target rows
+        self.rows = self.n // self.seg
+        self.seg_out = self.seg * L // M
+        self.total = probe._exact_count(self.n)
+        self.body = self.rows >= 2 and self.seg > 4 * self.H
+        self.done_in = self.rows * self.seg if self.body else 0
+        self.done_out = self.rows * self.seg_out if self.body else 0
+        self.f = FIRFilter(h, self.ratio, nchannels=self.rows, sample_dtype=self.tx, device=device) if self.body else None
+        self.g = FIRFilter(h, self.ratio, nchannels=1, sample_dtype=self.tx, device=device) if self.done_in < self.n else None
+        self._halo = None
+        self._idx = None
+
+    def run(self, x, halo0=None, out=None):
+        import torch
+        assert x.dim() == 1 and x.shape[0] == self.n
+        H, lib = self.H, _ffi.lib()
+        y = out if out is not None else torch.empty(self.total, dtype=x.dtype, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        k0 = C.c_int64()
+        if self.body:
+            body = x[:self.rows * self.seg].view(self.rows, self.seg)
+            if self._halo is None:
+                self._halo = torch.zeros((self.rows, max(H, 1)), dtype=x.dtype, device=x.device)
+                if H:
+                    self._idx = (torch.arange(1, self.rows, device=x.device) * self.seg).unsqueeze(1) + torch.arange(-H, 0, device=x.device)
+            if H:
+                self._halo[1:, :H] = x[self._idx]
+                if halo0 is not None:
+                    self._halo[0, :H] = halo0[-H:]
+                else:
+                    self._halo[0].zero_()
+            _ffi.check(lib.mrb_seek(self.f._handle, 0, self._halo.data_ptr() if H else None, max(H, 1), C.byref(k0), stream))
+            self.f.filt_(y[:self.rows * self.seg_out].view(self.rows, self.seg_out), body)
+        if self.g is not None:
+            halo = x[self.done_in - H:self.done_in].contiguous() if (self.done_in and H) else (
+                halo0[-H:].contiguous() if (halo0 is not None and H) else None)
+            _ffi.check(lib.mrb_seek(self.g._handle, self.done_in, halo.data_ptr() if halo is not None else None, H, C.byref(k0), stream))
+            assert k0.value == self.done_out
+            self.g.filt_(y[self.done_out:], x[self.done_in:])
+        return y
+
+
 def filt_long_stream(h, ratio, x, rows_target: int = 8192, halo0=None):
-    """One very long single-channel stream at multichannel speed, with no copy and no collective (SURVEY 8e,
-    BASELINE configs[4] "one 2^31-sample stream split into segments with tap-length halo").
-
-    The stream is viewed in place as a channel-major matrix of `rows` segments of `seg` samples, seg a multiple of the
-    decimation M: every segment then starts from the constructor state (phase 0, deficit 1; src/Filters.jl:567-571
-    in closed form), its history is simply the H samples that precede it in memory (the halo), and it produces exactly
-    seg*L/M outputs, so the output matrix is the output stream, in place.  The tail that does not fill a segment runs
-    through a one-channel filter seeked to its position.  x: 1-D CUDA tensor (torch); returns the 1-D output tensor.
-
-    Across GPUs the same call filters ONE RANK'S SEGMENT of the stream: give every rank a segment that starts at a
-    multiple of M (`segment_bounds(..., align=M)`) and pass `halo0` = the H samples that precede it (None for the
-    first segment).  A segment that starts at a multiple of M starts from the constructor state, so its outputs are
-    the stream's outputs [n0*L/M, ...) and no state or sample crosses between GPUs at run time.
-    """
-    import math
-    from fractions import Fraction
-
+    """One-call form of LongStream (plan and handles built per call).  x: 1-D CUDA tensor (torch); returns the 1-D output
+    tensor.  Across GPUs the same call filters ONE RANK'S SEGMENT of the stream: give every rank a segment that starts at a
+    multiple of M (`segment_bounds(..., align=M)`) and pass `halo0` = the H samples that precede it (None for the first)."""
     import numpy as np
-    import torch
-
-    from .filters import FIRFilter
-    ratio = Fraction(ratio)
-    L, M = ratio.numerator, ratio.denominator
-    n = x.shape[0]
     tx = np.dtype(str(x.dtype).replace("torch.", ""))
-    probe = FIRFilter(h, ratio, nchannels=1, sample_dtype=tx, device=-1)
-    H = probe.historyLen
-    # segment length: a multiple of M whose input and output row pitches are multiples of 16 bytes
-    al = max(1, 16 // tx.itemsize)
-    unit = M * al // math.gcd(M, al)
-    while (unit * L // M) % al:
-        unit *= 2
-    seg = max(unit, -(-(-(-n // max(rows_target, 1))) // unit) * unit)       # ceil: at most rows_target segments
-    rows = n // seg
-    seg_out = seg * L // M
-    total = probe._exact_count(n)
-    y = torch.empty(total, dtype=x.dtype, device=x.device)
-    stream = torch.cuda.current_stream(x.device).cuda_stream
-    lib = _ffi.lib()
-    done_in = done_out = 0
-    if rows >= 2 and seg > 4 * H:
-        body = x[:rows * seg].view(rows, seg)
-        f = FIRFilter(h, ratio, nchannels=rows, sample_dtype=tx, device=x.device.index or 0)
-        halo = torch.zeros((rows, max(H, 1)), dtype=x.dtype, device=x.device)
-        if H:
-            idx = (torch.arange(1, rows, device=x.device) * seg).unsqueeze(1) + torch.arange(-H, 0, device=x.device)
-            halo[1:, :H] = x[idx]
-            if halo0 is not None:
-                halo[0, :H] = halo0[-H:]
-        k0 = C.c_int64()
-        _ffi.check(lib.mrb_seek(f._handle, 0, halo.data_ptr() if H else None, max(H, 1), C.byref(k0), stream))
-        f.filt_(y[:rows * seg_out].view(rows, seg_out), body)
-        done_in, done_out = rows * seg, rows * seg_out
-    if done_in < n:
-        g = FIRFilter(h, ratio, nchannels=1, sample_dtype=tx, device=x.device.index or 0)
-        k0 = C.c_int64()
-        halo = x[done_in - H:done_in].contiguous() if (done_in and H) else (
-            halo0[-H:].contiguous() if (halo0 is not None and H) else None)
-        _ffi.check(lib.mrb_seek(g._handle, done_in, halo.data_ptr() if halo is not None else None, H, C.byref(k0), stream))
-        assert k0.value == done_out
-        g.filt_(y[done_out:], x[done_in:])
-    return y
+    return LongStream(h, ratio, x.shape[0], tx, device=x.device.index or 0, rows_target=rows_target).run(x, halo0)
