@@ -27,6 +27,8 @@ constexpr int kTabRows = 32;            // channels per CTA
 constexpr int kTabStep = 32;            // outputs per CTA step
 constexpr int kTabWarps = 4;
 constexpr int kTabGroup = 8;            // consecutive outputs that share one register window (one warp's share of a step)
+constexpr int kTabNB2 = 12;             // ring boxes of the two-channels-per-lane variant (64-row boxes of 8 KB)
+constexpr int kTabTB2 = 24;             // its tap block (Float64 samples): 24, or 22 when the rows fit
 
 // sample kinds the kernel is instantiated for
 enum { TAB_F32 = 0, TAB_F64 = 1, TAB_C64 = 2 };
@@ -113,30 +115,40 @@ struct alignas(16) TabParams {
 
 // TB = row elements (window samples) per tap block: TabCfg<K>::TB, or the next smaller size when the rows fit it
 // (every element of a row is a tap load and an FMA for all channels, zero padding included)
-template <int K, int TB>
-__global__ void __launch_bounds__(128, 3)
+// CH = channels per lane (the CTA is 32 CH channels wide).  CH = 2 (Float64): every broadcast tap load feeds the FMAs of two
+// channels -- the kernel is bound by shared-memory loads (90 % of the LSU at CH = 1), not by the FP64 pipe -- with tap
+// blocks of TB = 22/24 so that the two windows stay in registers (2 x 24 doubles) and ONE accumulator per output.
+// WPG = warps per window group of 8 outputs.  Measured on C4 Float64: two warps per group (8 warps per SM, 4 outputs each)
+// run 6 % SLOWER than one (64.0 against 68.0 Gout/s) -- the kernel is not short of warps, so WPG stays 1.
+constexpr int kTabWPG = 1;
+template <int K, int TB, int CH>
+__global__ void __launch_bounds__(128 * kTabWPG, CH == 1 ? 3 : 1)
 k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
             const typename TabCfg<K>::Tap *__restrict__ rows, const int32_t *__restrict__ astart,
             const __grid_constant__ TabParams P) {
     using C = TabCfg<K>;
     using R = typename C::Tap;
-    constexpr int A = C::A, NQ = TB / A, NB = C::NB, ES = C::ES;
-    static_assert(TB % 4 == 0 && TB <= C::TB, "tap rows are read four (two) at a time");
-    constexpr int BOX_BYTES = kTabRows * 128;
-    constexpr int OPW = kTabStep / kTabWarps;                        // outputs per warp per step
+    constexpr int A = C::A, NQ = TB / A, ES = C::ES;
+    constexpr int NB = CH == 1 ? C::NB : kTabNB2;                     // ring boxes
+    constexpr int ROWS = kTabRows * CH;                               // channels per CTA
+    static_assert(CH == 1 || K == TAB_F64, "two channels per lane: Float64 only");
+    static_assert(TB % 2 == 0 && TB <= C::TB, "tap rows are read four (two) at a time");
+    constexpr int BOX_BYTES = ROWS * 128;
+    constexpr int WPG = kTabWPG;                                     // warps per window group
+    constexpr int OPW = kTabStep / kTabWarps / WPG;                  // outputs per warp per step
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *out_buf = smem + NB * BOX_BYTES;                  // [32 ch][32 outputs], 128-byte swizzle atoms
     // the tap rows and aligned window starts of a step (32 outputs), double buffered, fetched by bulk copies a
     // step ahead: the taps are then read with warp-uniform LDS.128 instead of L2-latency global loads
     const int row_bytes = kTabStep * P.rowlen * (int)sizeof(R);      // R = tap type
-    unsigned char *rows_s = out_buf + kTabRows * kTabStep * ES;
+    unsigned char *rows_s = out_buf + ROWS * kTabStep * ES;
     int *ast_s = reinterpret_cast<int *>(rows_s + 2 * row_bytes);    // [2][32]
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(ast_s + 2 * kTabStep);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int ch0 = blockIdx.x * kTabRows;
+    const int ch0 = blockIdx.x * ROWS;
     const uint32_t in_base = smem_u32(smem), obase = smem_u32(out_buf), bar_base = smem_u32(bars);
     const uint32_t rbar_base = bar_base + 8 * NB;                    // two mbarriers for the staged rows
     const uint32_t rowpart = ((uint32_t)lane * 128u) ^ (((uint32_t)lane & 7u) << 4);   // SWIZZLE_128B
@@ -180,47 +192,73 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         const R *rows_step = reinterpret_cast<const R *>(rows_s + rslot * row_bytes);
         const int *ast_step = ast_s + rslot * kTabStep;
         {
-            static_assert(OPW == kTabGroup, "a warp's share of a step is one window group");
-            const long long kg = ks + warp * OPW;                    // first output of this warp's group
-            // f32 / f64: two partial sums per output; c64: real and imaginary part
+            static_assert(OPW * WPG == kTabGroup, "the warps of a group share one window");
+            const int grp = warp / WPG, sub = warp % WPG;            // window group of this warp, its part of the group
+            const long long kg = ks + grp * kTabGroup + sub * OPW;   // first output this warp computes
+            // f32 / f64: two partial sums per output; c64: real and imaginary part; CH = 2: one sum per output and channel
             R acc[OPW][2];
 #pragma unroll
             for (int o = 0; o < OPW; ++o) acc[o][0] = acc[o][1] = R(0);
             if (kg <= klast) {
-                const int a0 = ast_step[warp * OPW] - xbase;         // tile-relative aligned window start (samples)
+                const int a0 = ast_step[grp * kTabGroup] - xbase;    // tile-relative aligned window start (samples)
                 const int need = (a0 + P.rowlen - 1) / C::BOXE;
                 for (; j_waited <= need; ++j_waited) {
                     mbar_wait(bar_base + 8 * w_slot, w_par);
                     if (++w_slot == NB) { w_slot = 0; w_par ^= 1u; }
                 }
-                const R *rowg = rows_step + (warp * OPW) * P.rowlen;
+                const R *rowg = rows_step + (grp * kTabGroup + sub * OPW) * P.rowlen;
                 for (int bb = 0; bb < P.nblk; ++bb) {
                     const int p = ((a0 + bb * TB) / A) % (8 * NB);   // ring position in 16-byte chunks
-                    const unsigned *wt = P.win[p & 3] + (p & ~3);
-                    constexpr int WR = K == TAB_C64 ? 2 * TB : TB;   // window registers of type R
-                    R w[WR];
+                    constexpr int WR = K == TAB_C64 ? 2 * TB : TB;   // window registers of type R (per channel)
+                    R w[CH][WR];
+                    if constexpr (CH == 1) {
+                        const unsigned *wt = P.win[p & 3] + (p & ~3);
 #pragma unroll
-                    for (int q = 0; q < NQ; q += 4) {
-                        const uint4 w4 = *reinterpret_cast<const uint4 *>(wt + q);
-                        const unsigned ww[4] = {w4.x, w4.y, w4.z, w4.w};
+                        for (int q = 0; q < NQ; q += 4) {
+                            const uint4 w4 = *reinterpret_cast<const uint4 *>(wt + q);
+                            const unsigned ww[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (q + e >= NQ) break;
-                            const uint32_t ad = in_base + (rowpart ^ ww[e]);
-                            if constexpr (K == TAB_F64) {
-                                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
-                                             : "=d"(w[2 * (q + e)]), "=d"(w[2 * (q + e) + 1]) : "r"(ad) : "memory");
-                            } else {                                 // four floats: 4 real samples or 2 complex ones
-                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                             : "=f"(w[4 * (q + e)]), "=f"(w[4 * (q + e) + 1]), "=f"(w[4 * (q + e) + 2]),
-                                               "=f"(w[4 * (q + e) + 3]) : "r"(ad) : "memory");
+                            for (int e = 0; e < 4; ++e) {
+                                if (q + e >= NQ) break;
+                                const uint32_t ad = in_base + (rowpart ^ ww[e]);
+                                if constexpr (K == TAB_F64) {
+                                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                                                 : "=d"(w[0][2 * (q + e)]), "=d"(w[0][2 * (q + e) + 1]) : "r"(ad) : "memory");
+                                } else {                             // four floats: 4 real samples or 2 complex ones
+                                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=f"(w[0][4 * (q + e)]), "=f"(w[0][4 * (q + e) + 1]), "=f"(w[0][4 * (q + e) + 2]),
+                                                   "=f"(w[0][4 * (q + e) + 3]) : "r"(ad) : "memory");
+                                }
+                            }
+                        }
+                    } else {
+                        // ring position -> address word computed here (the CH = 1 table in the parameter block is laid out for
+                        // 32-row boxes): chunk u of the ring lives in box u >> 3, 16-byte chunk u & 7
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            int u = p + q;
+                            if (u >= 8 * NB) u -= 8 * NB;
+                            const uint32_t word = (uint32_t)((u & 7) << 4) | (uint32_t)((u >> 3) * BOX_BYTES);
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) {
+                                const uint32_t ad = in_base + ((rowpart + (uint32_t)(c * kTabRows * 128)) ^ word);
+                                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(w[c][2 * q]), "=d"(w[c][2 * q + 1]) : "r"(ad) : "memory");
                             }
                         }
                     }
 #pragma unroll
                     for (int o = 0; o < OPW; ++o) {
                         const R *tr = rowg + o * P.rowlen + bb * TB;
-                        if constexpr (K == TAB_F32) {
+                        if constexpr (CH == 2) {
+#pragma unroll
+                            for (int q = 0; q < TB / 2; ++q) {
+                                const double2 t = reinterpret_cast<const double2 *>(tr)[q];
+                                acc[o][0] = fma(t.x, w[0][2 * q], acc[o][0]);
+                                acc[o][1] = fma(t.x, w[1][2 * q], acc[o][1]);
+                                acc[o][0] = fma(t.y, w[0][2 * q + 1], acc[o][0]);
+                                acc[o][1] = fma(t.y, w[1][2 * q + 1], acc[o][1]);
+                            }
+                        } else if constexpr (K == TAB_F32) {
                             // the two partial sums of an output are one packed pair: (even taps, odd taps) x (even
                             // samples, odd samples) is one FFMA2 on two aligned register pairs -- half the issue slots
                             unsigned long long a2;
@@ -231,8 +269,8 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                                 unsigned long long t01, t23, w01, w23;
                                 asm("mov.b64 %0, {%1, %2};" : "=l"(t01) : "f"(t.x), "f"(t.y));
                                 asm("mov.b64 %0, {%1, %2};" : "=l"(t23) : "f"(t.z), "f"(t.w));
-                                asm("mov.b64 %0, {%1, %2};" : "=l"(w01) : "f"(w[4 * q]), "f"(w[4 * q + 1]));
-                                asm("mov.b64 %0, {%1, %2};" : "=l"(w23) : "f"(w[4 * q + 2]), "f"(w[4 * q + 3]));
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(w01) : "f"(w[0][4 * q]), "f"(w[0][4 * q + 1]));
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(w23) : "f"(w[0][4 * q + 2]), "f"(w[0][4 * q + 3]));
                                 asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a2) : "l"(t01), "l"(w01));
                                 asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a2) : "l"(t23), "l"(w23));
                             }
@@ -241,8 +279,8 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 #pragma unroll
                             for (int q = 0; q < TB / 2; ++q) {
                                 const double2 t = reinterpret_cast<const double2 *>(tr)[q];
-                                acc[o][0] = fma(t.x, w[2 * q], acc[o][0]);
-                                acc[o][1] = fma(t.y, w[2 * q + 1], acc[o][1]);
+                                acc[o][0] = fma(t.x, w[0][2 * q], acc[o][0]);
+                                acc[o][1] = fma(t.y, w[0][2 * q + 1], acc[o][1]);
                             }
                         } else {                                     // complex sample i = (w[2i], w[2i+1]), real tap
                             // one FFMA2 per tap: (re, im) += t * (re, im), the tap a scalar register operand
@@ -255,7 +293,7 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     unsigned long long xs;
-                                    asm("mov.b64 %0, {%1, %2};" : "=l"(xs) : "f"(w[8 * q + 2 * e]), "f"(w[8 * q + 2 * e + 1]));
+                                    asm("mov.b64 %0, {%1, %2};" : "=l"(xs) : "f"(w[0][8 * q + 2 * e]), "f"(w[0][8 * q + 2 * e + 1]));
                                     cfma(a2, tt[e], xs);
                                 }
                             }
@@ -267,10 +305,13 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
             // stage: row = channel, column = output within the step; 128-byte swizzle atoms of 32/16 outputs
 #pragma unroll
             for (int o = 0; o < OPW; ++o) {
-                const int col = warp * OPW + o;
+                const int col = grp * kTabGroup + sub * OPW + o;
                 const uint32_t byte = (uint32_t)col * ES;
-                const uint32_t ad = obase + (byte >> 7) * (kTabRows * 128u) + (rowpart ^ (((byte >> 4) & 7u) << 4)) + (byte & 15u);
-                if constexpr (K == TAB_F32) {
+                const uint32_t ad = obase + (byte >> 7) * (ROWS * 128u) + (rowpart ^ (((byte >> 4) & 7u) << 4)) + (byte & 15u);
+                if constexpr (CH == 2) {
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(acc[o][0]) : "memory");
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad + kTabRows * 128u), "d"(acc[o][1]) : "memory");
+                } else if constexpr (K == TAB_F32) {
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(acc[o][0] + acc[o][1]) : "memory");
                 } else if constexpr (K == TAB_F64) {
                     asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(acc[o][0] + acc[o][1]) : "memory");
@@ -289,7 +330,7 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         if (tid == 0) {
             constexpr int NST = kTabStep * ES / 128;                 // 128-byte-wide sub-boxes per step
             for (int b = 0; b < NST; ++b)
-                tma_store_2d(&tmy, (int)(P.y0 + ks) + b * C::BOXE, ch0, obase + (uint32_t)(b * kTabRows * 128));
+                tma_store_2d(&tmy, (int)(P.y0 + ks) + b * C::BOXE, ch0, obase + (uint32_t)(b * ROWS * 128));
             tma_commit();
             int sl = i_slot;
             for (int jj = j_issued; jj <= jtarget; ++jj) {
@@ -336,6 +377,7 @@ struct TabPlan {
     int K = TAB_F32;                   // sample kind the plan was built for
     int es = 4, ts = 4, A = 4, TB = 96, NB = 10;   // sample bytes, tap bytes, samples per 16 B, block, ring boxes
     int T = 0, nblk = 0, rowlen = 0;
+    int ch = 1;                        // channels per lane (2: Float64, the LSU-bound case)
     TabParams *hp = nullptr;
     PFN_encodeTiled encode = nullptr;
     int num_sms = 148;
@@ -348,7 +390,7 @@ static inline void table_release(TabPlan &p) {
 }
 
 static inline int table_smem(const TabPlan &p) {
-    return p.NB * kTabRows * 128 + kTabRows * kTabStep * p.es + 2 * kTabStep * p.rowlen * p.ts + 2 * kTabStep * 4 +
+    return p.NB * p.ch * kTabRows * 128 + p.ch * kTabRows * kTabStep * p.es + 2 * kTabStep * p.rowlen * p.ts + 2 * kTabStep * 4 +
            8 * (p.NB + 2);
 }
 
@@ -370,9 +412,18 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
     p.T = (int)T;
     // a group's rows are shifted by up to (A-1) + (window start of its last output - that of its first)
     const int64_t gspan = rate > 0.0 ? (int64_t)std::ceil((kTabGroup - 1) / rate) + 1 : (int64_t)1 << 20;
+    static const bool no2 = getenv("MRB_TABLE_CH1") != nullptr;
+    p.ch = (p.K == TAB_F64 && !no2) ? 2 : 1;
+    if (p.ch == 2) { p.TB = kTabTB2; p.NB = kTabNB2; }
     p.nblk = (int)ceil_div(T + p.A - 1 + gspan, p.TB);
-    if (p.nblk > 2) return 0;                                            // taps too long / rate too low for a shared window
-    {   // the next smaller block (22 instead of 24 16-byte chunks) when the rows still fit the same number of blocks
+    if (p.nblk > (p.ch == 2 ? 4 : 2)) {                                  // taps too long / rate too low for a shared window
+        if (p.ch == 2) {                                                 // (try the one-channel shape)
+            p.ch = 1; p.TB = TabCfg<TAB_F64>::TB; p.NB = TabCfg<TAB_F64>::NB;
+            p.nblk = (int)ceil_div(T + p.A - 1 + gspan, p.TB);
+        }
+        if (p.nblk > 2) return 0;
+    }
+    {   // the next smaller block (11 instead of 12 16-byte chunks per 24 taps) when the rows still fit the same number of blocks
         const int tbr = p.TB / 12 * 11;
         if (ceil_div(T + p.A - 1 + gspan, (int64_t)tbr) == p.nblk) p.TB = tbr;
     }
@@ -386,13 +437,18 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
             p.hp->win[c][i] = ((u & 7u) << 4) | ((u >> 3) * (unsigned)(kTabRows * 128));
         }
     const int smem = table_smem(p);
-    const bool red = p.TB != (p.K == TAB_F32 ? TabCfg<TAB_F32>::TB : TabCfg<TAB_F64>::TB);
-    e = p.K == TAB_F32 ? (red ? cudaFuncSetAttribute(k_table_fir<TAB_F32, 88>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                              : cudaFuncSetAttribute(k_table_fir<TAB_F32, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
-      : p.K == TAB_F64 ? (red ? cudaFuncSetAttribute(k_table_fir<TAB_F64, 44>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                              : cudaFuncSetAttribute(k_table_fir<TAB_F64, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
-                       : (red ? cudaFuncSetAttribute(k_table_fir<TAB_C64, 44>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                              : cudaFuncSetAttribute(k_table_fir<TAB_C64, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (smem > (int)prop.sharedMemPerBlockOptin) return 0;
+    const bool red = p.TB != (p.ch == 2 ? kTabTB2 : p.K == TAB_F32 ? TabCfg<TAB_F32>::TB : TabCfg<TAB_F64>::TB);
+    if (p.ch == 2)
+        e = red ? cudaFuncSetAttribute(k_table_fir<TAB_F64, 22, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                : cudaFuncSetAttribute(k_table_fir<TAB_F64, 24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    else
+    e = p.K == TAB_F32 ? (red ? cudaFuncSetAttribute(k_table_fir<TAB_F32, 88, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                              : cudaFuncSetAttribute(k_table_fir<TAB_F32, 96, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
+      : p.K == TAB_F64 ? (red ? cudaFuncSetAttribute(k_table_fir<TAB_F64, 44, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                              : cudaFuncSetAttribute(k_table_fir<TAB_F64, 48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
+                       : (red ? cudaFuncSetAttribute(k_table_fir<TAB_C64, 44, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                              : cudaFuncSetAttribute(k_table_fir<TAB_C64, 48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (e != cudaSuccess) return (int32_t)e;
     p.ok = true;
     return 0;
@@ -448,8 +504,8 @@ static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams 
     TabParams &P = *p.hp;
     P.k_begin = k_begin; P.N = cnt; P.y0 = y0;
     const int64_t span = cnt - k_begin;
-    const int64_t groups = ceil_div(G.nch, kTabRows);
-    int64_t tiles = std::max<int64_t>(1, std::min<int64_t>(span / (8 * kTabStep), ceil_div(6ll * 4 * p.num_sms, groups)));
+    const int64_t groups = ceil_div(G.nch, (int64_t)kTabRows * p.ch);
+    int64_t tiles = std::max<int64_t>(1, std::min<int64_t>(span / (8 * kTabStep), ceil_div((p.ch == 2 ? 4ll : 6ll * 4) * p.num_sms, groups)));
     P.KT = (int)(ceil_div(ceil_div(span, tiles), kTabStep) * kTabStep);
     tiles = ceil_div(span, P.KT);
 
@@ -458,7 +514,7 @@ static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams 
     const CUtensorMapDataType dt = es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     cuuint64_t dims[2] = {(cuuint64_t)G.n_in, (cuuint64_t)G.nch};
     cuuint64_t strides[1] = {(cuuint64_t)G.ldx * es};
-    cuuint32_t box[2] = {(cuuint32_t)BOXE, kTabRows};
+    cuuint32_t box[2] = {(cuuint32_t)BOXE, (cuuint32_t)(kTabRows * p.ch)};
     cuuint32_t ones[2] = {1, 1};
     if (p.encode(&tmx, dt, 2, const_cast<void *>(G.x), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -471,19 +527,22 @@ static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams 
 #undef MRB_TAB_SKIP
     dim3 grid((unsigned)groups, (unsigned)tiles);
     const int smem = table_smem(p);
-    const bool red = p.TB != (p.K == TAB_F32 ? TabCfg<TAB_F32>::TB : TabCfg<TAB_F64>::TB);
-    if (p.K == TAB_F32) {
-        if (red) k_table_fir<TAB_F32, 88><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
-        else k_table_fir<TAB_F32, 96><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
+    const bool red = p.TB != (p.ch == 2 ? kTabTB2 : p.K == TAB_F32 ? TabCfg<TAB_F32>::TB : TabCfg<TAB_F64>::TB);
+    if (p.ch == 2) {
+        if (red) k_table_fir<TAB_F64, 22, 2><<<grid, 128 * kTabWPG, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
+        else k_table_fir<TAB_F64, 24, 2><<<grid, 128 * kTabWPG, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
+    } else if (p.K == TAB_F32) {
+        if (red) k_table_fir<TAB_F32, 88, 1><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
+        else k_table_fir<TAB_F32, 96, 1><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
     } else if (p.K == TAB_F64) {
-        if (red) k_table_fir<TAB_F64, 44><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
-        else k_table_fir<TAB_F64, 48><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
+        if (red) k_table_fir<TAB_F64, 44, 1><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
+        else k_table_fir<TAB_F64, 48, 1><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
     } else {
-        if (red) k_table_fir<TAB_C64, 44><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
-        else k_table_fir<TAB_C64, 48><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
+        if (red) k_table_fir<TAB_C64, 44, 1><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
+        else k_table_fir<TAB_C64, 48, 1><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
     }
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
-    *name = p.K == TAB_F32 ? "table_f32" : p.K == TAB_F64 ? "table_f64" : "table_c64";
+    *name = p.K == TAB_F32 ? "table_f32" : p.K == TAB_F64 ? (p.ch == 2 ? "table_f64_2ch" : "table_f64") : "table_c64";
     ++*launches;
     return k_begin;
 }
