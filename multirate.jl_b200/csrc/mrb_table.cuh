@@ -121,8 +121,14 @@ struct alignas(16) TabParams {
 // WPG = warps per window group of 8 outputs.  Measured on C4 Float64: two warps per group (8 warps per SM, 4 outputs each)
 // run 6 % SLOWER than one (64.0 against 68.0 Gout/s) -- the kernel is not short of warps, so WPG stays 1.
 constexpr int kTabWPG = 1;
-template <int K, int TB, int CH>
-__global__ void __launch_bounds__(128 * kTabWPG, CH == 1 ? 3 : 1)
+// DM = 4 or 8 (Float64, CH = 2): the FP64 tensor-core variant with DM warps.  A group of 8 outputs x 8 channels is one
+// accumulator tile of mma.sync.m8n8k4.f64: A = the window [8 channels x 4 samples] (one LDS.64 per lane from the swizzled
+// ring, 2 wavefronts), B = the group's shifted tap rows [4 window positions x 8 outputs] (one LDS.64 per lane, the row
+// pitch = 4 mod 8 doubles keeps it at 2 wavefronts), reused by every channel octet of the warp.  Against DFMA this is one
+// instruction and 16 loaded bytes per 256 FMAs instead of per 32 / 64: the kernel leaves the LSU wall (DFMA and DMMA peak at
+// the same 37 TFLOP/s on this part, profiles/r2_dfma_probe.txt).  TB = 4 (one k-slice) in this variant.
+template <int K, int TB, int CH, int DM = 0>
+__global__ void __launch_bounds__(DM ? DM * 32 : 128 * kTabWPG, CH == 1 ? 3 : 1)
 k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
             const typename TabCfg<K>::Tap *__restrict__ rows, const int32_t *__restrict__ astart,
             const __grid_constant__ TabParams P) {
@@ -133,6 +139,7 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     constexpr int ROWS = kTabRows * CH;                               // channels per CTA
     static_assert(CH == 1 || K == TAB_F64, "two channels per lane: Float64 only");
     static_assert(TB % 2 == 0 && TB <= C::TB, "tap rows are read four (two) at a time");
+    static_assert(DM == 0 || (CH == 2 && TB == 4 && (DM == 4 || DM == 8)), "tensor-core variant: 64-channel CTAs, k-slices of 4");
     constexpr int BOX_BYTES = ROWS * 128;
     constexpr int WPG = kTabWPG;                                     // warps per window group
     constexpr int OPW = kTabStep / kTabWarps / WPG;                  // outputs per warp per step
@@ -141,7 +148,12 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     // the tap rows and aligned window starts of a step (32 outputs), double buffered, fetched by bulk copies a
     // step ahead: the taps are then read with warp-uniform LDS.128 instead of L2-latency global loads
     const int row_bytes = kTabStep * P.rowlen * (int)sizeof(R);      // R = tap type
-    unsigned char *rows_s = out_buf + ROWS * kTabStep * ES;
+    // DB: two staging buffers and ONE CTA barrier per step (the tensor-core variant, one CTA per SM: a warp that waits at a
+    // barrier is a quarter of the SM idle) -- thread 0 makes sure the previous step's store has left its buffer BEFORE the
+    // barrier, issues this step's store after it and does not wait for it
+    constexpr bool DB = DM != 0;
+    constexpr int STG_BYTES = ROWS * kTabStep * ES;
+    unsigned char *rows_s = out_buf + (DB ? 2 : 1) * STG_BYTES;
     int *ast_s = reinterpret_cast<int *>(rows_s + 2 * row_bytes);    // [2][32]
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(ast_s + 2 * kTabStep);
 
@@ -191,7 +203,68 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         mbar_wait(rbar_base + 8 * rslot, (uint32_t)((s >> 1) & 1));  // this step's tap rows are in shared memory
         const R *rows_step = reinterpret_cast<const R *>(rows_s + rslot * row_bytes);
         const int *ast_step = ast_s + rslot * kTabStep;
-        {
+        if constexpr (DM != 0) {
+            // ---- FP64 tensor cores: warp = (group of 8 outputs, DM == 8: half of the channels)
+            constexpr int CB = DM == 4 ? 8 : 4;                      // channel octets per warp
+            const int grp = warp & 3, half = DM == 4 ? 0 : warp >> 2;
+            const int r = lane >> 2, kq = lane & 3;                  // fragment row (channel / output), k index
+            // fragment row r <-> channel rr of the octet: a 64-bit shared load is served per half warp (fragment rows 0..3),
+            // whose four 32-byte reads must fall into four different chunk pairs of the 128-byte swizzle: rows 0, 2, 4, 6
+            // (rows 0..3 share two pairs: every A load cost 4 wavefronts instead of 2)
+            const int rr = ((r & 3) << 1) | (r >> 2);
+            const long long kg = ks + grp * kTabGroup;
+            double acc[CB][2];
+#pragma unroll
+            for (int c = 0; c < CB; ++c) acc[c][0] = acc[c][1] = 0.0;
+            if (kg <= klast) {
+                const int a0 = ast_step[grp * kTabGroup] - xbase;    // tile-relative aligned window start (even)
+                const int need = (a0 + P.rowlen - 1) / C::BOXE;
+                for (; j_waited <= need; ++j_waited) {
+                    mbar_wait(bar_base + 8 * w_slot, w_par);
+                    if (++w_slot == NB) { w_slot = 0; w_par ^= 1u; }
+                }
+                // B fragment: lane (k = kq, n = r) reads row r of the group at window position 4 kk + kq
+                const uint32_t bp = smem_u32(rows_step) + (uint32_t)(((grp * kTabGroup + r) * P.rowlen + kq) * 8);
+                // A fragment: lane (m = r, k = kq) reads channel 8 c + r at sample a0 + 4 kk + kq: ring chunk u, half kq & 1
+                int u = (a0 >> 1) % (8 * NB) + (kq >> 1);
+                const uint32_t abase = in_base + (uint32_t)(half * (CB * 8 * 128) + rr * 128 + (kq & 1) * 8);
+                // software pipeline: the fragments of slice kk + 1 are in flight while the tensor pipe works on slice kk
+                auto load_slice = [&](int kk, double &b, double (&a)[CB]) {
+                    if (u >= 8 * NB) u -= 8 * NB;
+                    const uint32_t ad = abase + (uint32_t)((((u & 7) ^ rr) << 4) + (u >> 3) * BOX_BYTES);
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b) : "r"(bp + (uint32_t)(kk * 32)) : "memory");
+#pragma unroll
+                    for (int c = 0; c < CB; ++c)
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[c]) : "r"(ad + (uint32_t)(c * 8 * 128)) : "memory");
+                    u += 2;
+                };
+                double b0, a0f[CB], b1, a1f[CB];
+                load_slice(0, b0, a0f);
+                for (int kk = 0; kk < P.nblk; kk += 2) {             // nblk is odd: the second half of the last pair is skipped
+                    const bool more = kk + 1 < P.nblk;
+                    if (more) load_slice(kk + 1, b1, a1f);
+#pragma unroll
+                    for (int c = 0; c < CB; ++c)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(acc[c][0]), "+d"(acc[c][1]) : "d"(a0f[c]), "d"(b0));
+                    if (!more) break;
+                    if (kk + 2 < P.nblk) load_slice(kk + 2, b0, a0f);
+#pragma unroll
+                    for (int c = 0; c < CB; ++c)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(acc[c][0]), "+d"(acc[c][1]) : "d"(a1f[c]), "d"(b1));
+                }
+            }
+            // stage: lane holds channel 8 c + rr, outputs 2 kq and 2 kq + 1 of the group
+            const uint32_t byte = (uint32_t)(grp * kTabGroup + 2 * kq) * 8u;
+#pragma unroll
+            for (int c = 0; c < CB; ++c) {
+                const uint32_t row = (uint32_t)(half * CB * 8 + c * 8 + rr);
+                const uint32_t ad = obase + (uint32_t)((s & 1) * STG_BYTES) + (byte >> 7) * (ROWS * 128u) + row * 128u +
+                                    ((((byte >> 4) & 7u) ^ (row & 7u)) << 4);
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ad), "d"(acc[c][0]), "d"(acc[c][1]) : "memory");
+            }
+        } else {
             static_assert(OPW * WPG == kTabGroup, "the warps of a group share one window");
             const int grp = warp / WPG, sub = warp % WPG;            // window group of this warp, its part of the group
             const long long kg = ks + grp * kTabGroup + sub * OPW;   // first output this warp computes
@@ -323,6 +396,30 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 
         // ---- the step's outputs leave; boxes before the next step's first window are refilled
         fence_async_smem();
+        if constexpr (DB) {
+            if (tid == 0) tma_wait_read<0>();              // the previous step's store has left the other staging buffer
+            __syncthreads();
+            if (tid == 0) {
+                constexpr int NST = kTabStep * ES / 128;
+                for (int b = 0; b < NST; ++b)
+                    tma_store_2d(&tmy, (int)(P.y0 + ks) + b * C::BOXE, ch0, obase + (uint32_t)((s & 1) * STG_BYTES + b * ROWS * 128));
+                tma_commit();
+                int jtarget = jlast;
+                if (s + 1 < nsteps) {                      // the next step's first window start is already in shared memory
+                    mbar_wait(rbar_base + 8 * (rslot ^ 1), (uint32_t)(((s + 1) >> 1) & 1));
+                    jtarget = min((ast_s[(rslot ^ 1) * kTabStep] - xbase) / C::BOXE + NB - 1, jlast);
+                }
+                for (int jj = j_issued; jj <= jtarget; ++jj) {
+                    const uint32_t bar = bar_base + 8 * i_slot;
+                    mbar_expect_tx(bar, BOX_BYTES);
+                    tma_load_2d(in_base + (uint32_t)(i_slot * BOX_BYTES), &tmx, xbase + jj * C::BOXE, ch0, bar);
+                    if (++i_slot == NB) i_slot = 0;
+                }
+                if (jtarget >= j_issued) j_issued = jtarget + 1;
+                if (s + 2 < nsteps) stage_rows(ks + 2 * kTabStep, rslot);
+            }
+            continue;
+        }
         __syncthreads();
         const long long kn = min(ks + kTabStep, klast);
         const int jdead = (astart[kn] - xbase) / C::BOXE;            // oldest box the next step reads
@@ -349,7 +446,8 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         }
         __syncthreads();
     }
-    for (; j_waited < j_issued; ++j_waited) {             // every issued load must have landed before exit
+    if (DB && tid == 0) tma_wait_read<0>();               // the last store still reads its staging buffer
+    for (; j_waited < j_issued; ++j_waited) {             // every issued load must have landed before exit (DB: thread 0 knows)
         mbar_wait(bar_base + 8 * w_slot, w_par);
         if (++w_slot == NB) { w_slot = 0; w_par ^= 1u; }
     }
@@ -378,6 +476,7 @@ struct TabPlan {
     int es = 4, ts = 4, A = 4, TB = 96, NB = 10;   // sample bytes, tap bytes, samples per 16 B, block, ring boxes
     int T = 0, nblk = 0, rowlen = 0;
     int ch = 1;                        // channels per lane (2: Float64, the LSU-bound case)
+    int dm = 0;                        // warps of the FP64 tensor-core variant (0: CUDA cores)
     TabParams *hp = nullptr;
     PFN_encodeTiled encode = nullptr;
     int num_sms = 148;
@@ -390,7 +489,7 @@ static inline void table_release(TabPlan &p) {
 }
 
 static inline int table_smem(const TabPlan &p) {
-    return p.NB * p.ch * kTabRows * 128 + p.ch * kTabRows * kTabStep * p.es + 2 * kTabStep * p.rowlen * p.ts + 2 * kTabStep * 4 +
+    return p.NB * p.ch * kTabRows * 128 + (p.dm ? 2 : 1) * p.ch * kTabRows * kTabStep * p.es + 2 * kTabStep * p.rowlen * p.ts + 2 * kTabStep * 4 +
            8 * (p.NB + 2);
 }
 
@@ -414,6 +513,17 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
     const int64_t gspan = rate > 0.0 ? (int64_t)std::ceil((kTabGroup - 1) / rate) + 1 : (int64_t)1 << 20;
     static const bool no2 = getenv("MRB_TABLE_CH1") != nullptr;
     p.ch = (p.K == TAB_F64 && !no2) ? 2 : 1;
+    p.dm = 0;
+    if (p.ch == 2) {
+        // FP64 tensor cores (mma.sync m8n8k4): k-slices of 4, row pitch = 4 mod 8 doubles (conflict-free fragment loads)
+        static const char *nd = getenv("MRB_NO_DMMA"), *dw = getenv("MRB_DMMA_WARPS");
+        int64_t rl = T + p.A - 1 + gspan;
+        rl = (rl + 3) / 8 * 8 + 4;
+        TabPlan q = p;
+        q.dm = dw && atoi(dw) == 4 ? 4 : 8; q.TB = 4; q.NB = kTabNB2; q.rowlen = (int)rl; q.nblk = (int)(rl / 4);
+        if (!nd && rl <= 256 && table_smem(q) <= (int)prop.sharedMemPerBlockOptin) p = q;
+    }
+    if (p.dm == 0) {
     if (p.ch == 2) { p.TB = kTabTB2; p.NB = kTabNB2; }
     p.nblk = (int)ceil_div(T + p.A - 1 + gspan, p.TB);
     if (p.nblk > (p.ch == 2 ? 4 : 2)) {                                  // taps too long / rate too low for a shared window
@@ -427,6 +537,7 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
         const int tbr = p.TB / 12 * 11;
         if (ceil_div(T + p.A - 1 + gspan, (int64_t)tbr) == p.nblk) p.TB = tbr;
     }
+    }
     p.rowlen = p.nblk * p.TB;
     p.hp = new TabParams();
     memset(p.hp, 0, sizeof(TabParams));
@@ -439,7 +550,10 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
     const int smem = table_smem(p);
     if (smem > (int)prop.sharedMemPerBlockOptin) return 0;
     const bool red = p.TB != (p.ch == 2 ? kTabTB2 : p.K == TAB_F32 ? TabCfg<TAB_F32>::TB : TabCfg<TAB_F64>::TB);
-    if (p.ch == 2)
+    if (p.dm)
+        e = p.dm == 4 ? cudaFuncSetAttribute(k_table_fir<TAB_F64, 4, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                      : cudaFuncSetAttribute(k_table_fir<TAB_F64, 4, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    else if (p.ch == 2)
         e = red ? cudaFuncSetAttribute(k_table_fir<TAB_F64, 22, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
                 : cudaFuncSetAttribute(k_table_fir<TAB_F64, 24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     else
@@ -528,7 +642,11 @@ static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams 
     dim3 grid((unsigned)groups, (unsigned)tiles);
     const int smem = table_smem(p);
     const bool red = p.TB != (p.ch == 2 ? kTabTB2 : p.K == TAB_F32 ? TabCfg<TAB_F32>::TB : TabCfg<TAB_F64>::TB);
-    if (p.ch == 2) {
+    if (p.dm == 4) {
+        k_table_fir<TAB_F64, 4, 2, 4><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
+    } else if (p.dm == 8) {
+        k_table_fir<TAB_F64, 4, 2, 8><<<grid, 256, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
+    } else if (p.ch == 2) {
         if (red) k_table_fir<TAB_F64, 22, 2><<<grid, 128 * kTabWPG, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
         else k_table_fir<TAB_F64, 24, 2><<<grid, 128 * kTabWPG, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
     } else if (p.K == TAB_F32) {
@@ -542,7 +660,7 @@ static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams 
         else k_table_fir<TAB_C64, 48, 1><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
     }
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
-    *name = p.K == TAB_F32 ? "table_f32" : p.K == TAB_F64 ? (p.ch == 2 ? "table_f64_2ch" : "table_f64") : "table_c64";
+    *name = p.K == TAB_F32 ? "table_f32" : p.K == TAB_F64 ? (p.dm ? "table_f64_dmma" : p.ch == 2 ? "table_f64_2ch" : "table_f64") : "table_c64";
     ++*launches;
     return k_begin;
 }

@@ -6,6 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import multirate_b200 as mr, multirate_oracle as mo
 w = sys.argv[1]
+dt = np.float64 if w.endswith("64") else np.float32
+w = w[:-2] if w.endswith("64") else w
 N = 32
 hl, beta = mo.kaiserlength(0.05, samplerate=N); hl = -(-hl // N) * N
 cfg = {"c3b": (Fraction(1, 1), mo.firdes(128, 0.25, 7.8562), 4096, ()), "c3a": (Fraction(4, 1), mo.firdes(128, 0.125, 7.8562) * 4, 4096, ()),
@@ -14,8 +16,8 @@ cfg = {"c3b": (Fraction(1, 1), mo.firdes(128, 0.25, 7.8562), 4096, ()), "c3a": (
 ratio, h, nch, extra = cfg
 if len(sys.argv) > 2:
     nch = int(sys.argv[2])
-x = torch.rand((nch, 65536), device="cuda")
-f = mr.FIRFilter(h.astype(np.float32), ratio, *extra, nchannels=nch, sample_dtype=np.float32)
+x = torch.rand((nch, 65536), device="cuda", dtype=torch.float64 if dt is np.float64 else torch.float32)
+f = mr.FIRFilter(h.astype(dt), ratio, *extra, nchannels=nch, sample_dtype=dt)
 for _ in range(4):
     f.filt(x)
 torch.cuda.synchronize()
