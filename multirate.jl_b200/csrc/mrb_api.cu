@@ -115,6 +115,10 @@ struct TableCtx {
     void *d_taptab = nullptr;          // farrow: R[kSchedChunk][T]
     TabRows rows;                      // table kernel: tap rows + aligned window starts of one slice
     MmaRows mrows;                     // tensor-core kernel: tap tiles + group window starts of one slice
+    // the slice's head (outputs whose windows reach the history: k_head_warp / k_generic) runs on a side stream beside
+    // the main kernel, which leaves issue slots free (one CTA per SM); forked and joined with events, no host wait
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 constexpr int kMaxHostStreams = 4;
 
@@ -207,6 +211,9 @@ static void free_device(mrb_filter *f) {
         cudaFree(c.d_taptab); c.d_taptab = nullptr;
         tabrows_release(c.rows);
         mmarows_release(c.mrows);
+        if (c.side) { cudaStreamDestroy(c.side); c.side = nullptr; }
+        if (c.ev_fork) { cudaEventDestroy(c.ev_fork); c.ev_fork = nullptr; }
+        if (c.ev_join) { cudaEventDestroy(c.ev_join); c.ev_join = nullptr; }
         c.ready = false;
     }
     cudaFree(f->d_xs); cudaFree(f->d_ys);
@@ -961,6 +968,12 @@ static int32_t ensure_sched(mrb_filter *f, TableCtx &c) {
     }
     if (f->kind == MRB_FARROW)
         CU(cudaMalloc(&c.d_taptab, (size_t)kSchedChunk * f->T * (is_double(f->ty) ? 8 : 4)));
+    static const bool no_side = getenv("MRB_NO_SIDE_STREAM") != nullptr;
+    if (!no_side && !f->mma.ok) {      // (the tensor-core kernel computes its head itself)
+        CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    }
     c.ready = true;
     return MRB_OK;
 }
@@ -1044,6 +1057,8 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 if (k0 + cnt >= N) { CU(cudaEventRecord(store.ev, st)); store.pending = true; }   // the store is free again after this
                 P.sn = s.d_n; P.k_base = k0; P.nout = cnt;
                 P.sphi = s.d_phi; P.salpha = s.d_a;
+                cudaStream_t hs = st;                          // stream of the slice's head
+                if (f->policy != 1 && tc.side) CU(cudaEventRecord(tc.ev_fork, st));
                 if (f->policy != 1) {
                     // fast path: per-output tap rows built once for all channels, then one dot product per output
                     int64_t head = 0;                          // outputs of the slice whose window reaches the history
@@ -1068,8 +1083,12 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                                                         &f->launches);
                     if (kb == -2) return fail(MRB_ERR_CUDA, "table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                     if (kb == 0) continue;
-                    if (kb > 0) P.nout = kb;                   // the generic kernel computes the slice's head
-                    else f->last_kernel = "generic";
+                    if (kb > 0) {                              // the generic kernel computes the slice's head
+                        P.nout = kb;
+                        if (tc.side) { CU(cudaStreamWaitEvent(tc.side, tc.ev_fork, 0)); hs = tc.side; }
+                    } else {
+                        f->last_kernel = "generic";
+                    }
                 } else {
                     f->last_kernel = "generic";
                 }
@@ -1080,13 +1099,14 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                     // tap rows for the outputs the generic kernel computes: the whole slice, or only its head
                     const unsigned g = (unsigned)ceil_div(P.nout * f->T, 256);
                     if (is_double(f->ty))
-                        k_farrow_taps<double><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, P.nout, (double *)tc.d_taptab, f->th == MRB_F32);
+                        k_farrow_taps<double><<<g, 256, 0, hs>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, P.nout, (double *)tc.d_taptab, f->th == MRB_F32);
                     else
-                        k_farrow_taps<float><<<g, 256, 0, st>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, P.nout, (float *)tc.d_taptab, f->th == MRB_F32);
+                        k_farrow_taps<float><<<g, 256, 0, hs>>>(f->d_pnfb, f->polyorder + 1, f->T, s.d_a, P.nout, (float *)tc.d_taptab, f->th == MRB_F32);
                     ++f->launches;
                 }
-                dispatch_generic(f, P, st);
+                dispatch_generic(f, P, hs);
                 ++f->launches;
+                if (hs != st) { CU(cudaEventRecord(tc.ev_join, hs)); CU(cudaStreamWaitEvent(st, tc.ev_join, 0)); }
             }
         }
     }
