@@ -519,6 +519,7 @@ static int32_t set_taps_impl(mrb_filter *f, const void *hv, int64_t h_len, const
         // parameter-block kernels: their host blocks (copied into every launch)
         tiled_set_bank(f->tiled, f->L, f->T, bank);
         unit_set_bank(f->unit, f->T, bank);
+        decim8_set_bank(f->decim, bank);
         f->last_stream = st; f->last_valid = true;
     }
     f->bank.swap(bank);

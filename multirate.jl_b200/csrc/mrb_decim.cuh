@@ -218,6 +218,136 @@ k_decim(const __grid_constant__ CUtensorMap tmx, void *__restrict__ yv, long lon
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// k_decim8: M = 8, complex64 -- lane = channel, taps = launch constants
+// ---------------------------------------------------------------------------------------------------------
+// k_decim above spends a quarter of its FMA-pipe cycles and 40 % of its issue slots on everything that is not an FFMA2
+// (window addressing, the shuffle reduce-scatter with its selects) and re-reads its window five times.  Here a LANE is
+// one channel (16 channels x 2 output blocks per warp) and computes 8 consecutive outputs from a 320-sample window read
+// ONCE with LDS.128 (two complex samples, [16 ch][16 samples] boxes with the 128-byte swizzle: conflict free), with
+//     acc[r] += h[8 (m - r) + q] * x[8 m + q]        r = 0..7 outputs, window position 8 m + q
+// fully unrolled: every tap is a compile-time offset into the kernel's parameter block, i.e. a constant-bank operand
+// fetched by the uniform datapath (LDCU) -- no tap registers, no tap loads on the LSU, no cross-lane reduction, 13 FFMA2
+// per shared-memory load.  The price is shared memory: the outputs in flight need their 8 new samples each (64 B per
+// output and channel), so an SM holds 4 warps x 32 lanes x 8 outputs = 64 KB of new samples per step, in a ring of three
+// 64 KB super-groups (512 samples x 16 channels) with one full and one empty mbarrier each: a step reads super-groups s
+// and s+1 while the producer warp fills s+2.  One CTA (4 consumer warps + producer) per SM; latency is hidden inside the
+// warp (8 independent accumulators, loads hoisted by the compiler over the static schedule).
+constexpr int kD8Ch = 16;               // channels per CTA
+constexpr int kD8Step = 64;             // outputs per channel and CTA step
+constexpr int kD8TQ = 33;               // tap slots per residue (T <= 256, one slot of slack for the alignment shift)
+constexpr int kD8SG = 65536;            // bytes per super-group: 512 samples x 16 channels x 8 B = 32 boxes of 2 KB
+constexpr int kD8Smem = 3 * kD8SG + 64;
+
+struct alignas(16) Dec8Params {
+    long long k_begin, N;      // this launch covers outputs [k_begin, N)
+    long long e;               // x index of the first sample of output 0's padded window (even)
+    int KT, pad;               // outputs per tile (multiple of 64)
+    float hq[4][kD8TQ][2];     // hq[c][j][b] = padded hflip[8 j + 2 c + b]
+};
+
+__global__ void __launch_bounds__(160, 1)
+k_decim8(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, long long ldy, int nch,
+         const __grid_constant__ Dec8Params P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ring = smem_u32(smem), full = ring + 3 * kD8SG, empty = full + 24;
+    const int ch0 = blockIdx.y * kD8Ch;
+    const long long k0 = P.k_begin + (long long)blockIdx.x * P.KT;
+    const int ntile = (int)min((long long)P.KT, P.N - k0);
+    const int nsteps = (ntile + kD8Step - 1) / kD8Step;
+    const long long x0 = P.e + k0 * 8;                               // x index of the tile's first sample (even, >= 0)
+
+    if (tid == 0) {
+        if (ring & 1023u) __trap();
+        for (int i = 0; i < 3; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
+    }
+    __syncthreads();
+
+    if (warp == 4) {
+        // ---- producer: super-group sg = samples [512 sg, 512 sg + 512) of the tile; the last one is read only in its
+        // first 256 samples (the window tail of the last step)
+        if (lane == 0) {
+            for (int sg = 0; sg <= nsteps; ++sg) {
+                const int slot = sg % 3;
+                if (sg >= 3) mbar_wait(empty + 8 * slot, (uint32_t)((sg / 3 - 1) & 1));
+                const int nbox = sg == nsteps ? 16 : 32;
+                mbar_expect_tx(full + 8 * slot, (uint32_t)(nbox * 2048));
+                for (int bx = 0; bx < nbox; ++bx)
+                    tma_load_2d(ring + (uint32_t)(slot * kD8SG + bx * 2048), &tmx, (int)((x0 + sg * 512 + bx * 16) * 2), ch0,
+                                full + 8 * slot);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: warp (a, b), lane half hb -> outputs 8 o .. 8 o + 7 of the step, o = 4 a + 2 hb + b; the lane's
+    // window is the five 64-sample groups o .. o + 4 of the step (8 groups per super-group)
+    const int chl = lane & 15, hb = lane >> 4;
+    const int o = 4 * (warp >> 1) + 2 * hb + (warp & 1);
+    const int c_glob = ch0 + chl;
+    float2 *yrow = y + (long long)c_glob * ldy;
+
+    mbar_wait(full, 0u);
+    for (int s = 0; s < nsteps; ++s) {
+        mbar_wait(full + 8 * (uint32_t)((s + 1) % 3), (uint32_t)(((s + 1) / 3) & 1));
+        uint32_t base[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int gg = o + i;
+            base[i] = ring + (uint32_t)(((s + (gg >> 3)) % 3) * kD8SG + (gg & 7) * 8192);
+        }
+        unsigned long long acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = 0ull;
+        // the q-pair loop is NOT unrolled: 2112 FFMA2 of straight-line code (40 KB) miss the 32 KB instruction cache (18 % of
+        // the issue slots went to "no instruction"); per q-pair the 66 taps are fetched with a uniform base offset
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t xe = (uint32_t)(chl * 128 + ((c ^ (chl & 7)) << 4));           // chunk c of the lane's row (m even)
+            const uint32_t xo = (uint32_t)(chl * 128 + (((4 + c) ^ (chl & 7)) << 4));     // chunk 4 + c (m odd)
+#pragma unroll
+            for (int m = 0; m < 40; ++m) {
+                // window position 8 m + 2 c (+1): group m / 8, box (m % 8) / 2, chunk 4 (m & 1) + c
+                const uint32_t ad = base[m >> 3] + (uint32_t)(((m & 7) >> 1) * 2048) + ((m & 1) ? xo : xe);
+                unsigned long long xa, xb;
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xa), "=l"(xb) : "r"(ad) : "memory");
+                // eight independent accumulators in a row, then the second sample: no back-to-back dependent FFMA2
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (m - r >= 0 && m - r < kD8TQ) cfma(acc[r], P.hq[c][m - r][0], xa);
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (m - r >= 0 && m - r < kD8TQ) cfma(acc[r], P.hq[c][m - r][1], xb);
+            }
+        }
+        // ---- 8 consecutive outputs of one channel: 64 contiguous bytes
+        const long long k = k0 + (long long)s * kD8Step + 8 * o;
+        if (c_glob < nch) {
+            if (k + 8 <= P.N && ((reinterpret_cast<uintptr_t>(yrow + k) & 15) == 0)) {
+#pragma unroll
+                for (int r = 0; r < 8; r += 2) {
+                    float4 v;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(acc[r]));
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(acc[r + 1]));
+                    *reinterpret_cast<float4 *>(yrow + k + r) = v;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    float2 v;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(acc[r]));
+                    if (k + r < P.N) yrow[k + r] = v;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty + 8 * (uint32_t)(s % 3)) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 struct DecPlan {
@@ -229,11 +359,32 @@ struct DecPlan {
     float *d_taps = nullptr;
     PFN_encodeTiled encode = nullptr;
     int num_sms = 148;
+    // k_decim8 (M = 8, complex64): the padded taps for both alignments, copied into every launch's parameter block
+    bool d8 = false;
+    Dec8Params *hp8 = nullptr;
+    float h8[2][4][kD8TQ][2];
 };
+
+// hq tables of k_decim8 from the flipped taps (bank[i] multiplies window sample i)
+static inline void decim8_set_bank(DecPlan &p, const std::vector<double> &bank) {
+    if (!p.d8) return;
+    memset(p.h8, 0, sizeof(p.h8));
+    const int64_t Tp = (int64_t)kD8TQ * 8;
+    for (int64_t delta = 0; delta < 2; ++delta) {
+        const int64_t zf = Tp - p.T - delta;
+        for (int64_t i = 0; i < p.T; ++i) {
+            const int64_t ip = i + zf;
+            p.h8[delta][(ip & 7) >> 1][ip >> 3][ip & 1] = (float)bank[(size_t)i];
+        }
+    }
+}
 
 static inline void decim_release(DecPlan &p) {
     delete p.hp;
     p.hp = nullptr;
+    delete p.hp8;
+    p.hp8 = nullptr;
+    p.d8 = false;
     cudaFree(p.d_taps);
     p.d_taps = nullptr;
     p.ok = false;
@@ -282,6 +433,15 @@ static inline int32_t decim_prepare(DecPlan &p, int kind, int tx, int ty, int64_
         else e = cudaFuncSetAttribute(k_decim<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<8, false>::SMEM);
     }
     if (e != cudaSuccess) return (int32_t)e;
+    static const bool no8 = getenv("MRB_DECIM8") && atoi(getenv("MRB_DECIM8")) == 0;
+    if (p.cplx && M == 8 && !no8 && kD8Smem <= (int)prop.sharedMemPerBlockOptin) {
+        e = cudaFuncSetAttribute(k_decim8, cudaFuncAttributeMaxDynamicSharedMemorySize, kD8Smem);
+        if (e != cudaSuccess) return (int32_t)e;
+        p.hp8 = new Dec8Params();
+        memset(p.hp8, 0, sizeof(Dec8Params));
+        p.d8 = true;
+        decim8_set_bank(p, bank);
+    }
     p.ok = true;
     return 0;
 }
@@ -331,9 +491,40 @@ static inline int64_t decim_try_launch(DecPlan &p, const GenParams &G, cudaStrea
     k_begin = (k_begin + 7) / 8 * 8;                           // whole steps: k_begin*M keeps e + k_begin*M aligned
     if (G.nout - k_begin < 64) MRB_DEC_SKIP("chunk too short");
 
+    const int64_t span = G.nout - k_begin;
+    if (p.d8 && ceil_div(G.nch, kD8Ch) * (span / kD8Step) >= 2 * p.num_sms && ((uintptr_t)G.y & 7) == 0) {
+        // ---- lane-per-channel kernel with launch-constant taps
+        Dec8Params &P8 = *p.hp8;
+        P8.k_begin = k_begin; P8.N = G.nout; P8.e = e;
+        memcpy(P8.hq, p.h8[delta], sizeof(P8.hq));
+        const int64_t groups8 = ceil_div(G.nch, kD8Ch);
+        // tiles per channel group: whole waves of one CTA per SM, each tile pays about 1.5 steps of ring fill
+        int64_t best_t = 1;
+        double best = 1e300;
+        for (int64_t t = 1; t <= std::min<int64_t>(span / kD8Step, 256); ++t) {
+            const int64_t steps = ceil_div(ceil_div(span, t), kD8Step);
+            const double cost = (double)ceil_div(t * groups8, p.num_sms) * ((double)steps + 1.5);
+            if (cost < best) { best = cost; best_t = t; }
+        }
+        P8.KT = (int)(ceil_div(ceil_div(span, best_t), kD8Step) * kD8Step);
+        const int64_t tiles8 = ceil_div(span, P8.KT);
+        CUtensorMap tm8;
+        cuuint64_t dims[2] = {(cuuint64_t)(2 * G.n_in), (cuuint64_t)G.nch};
+        cuuint64_t strides[1] = {(cuuint64_t)G.ldx * 8};
+        cuuint32_t box[2] = {32, (cuuint32_t)kD8Ch};
+        cuuint32_t es[2] = {1, 1};
+        if (p.encode(&tm8, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(G.x), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            MRB_DEC_SKIP("x tensor map");
+        k_decim8<<<dim3((unsigned)tiles8, (unsigned)groups8), 160, kD8Smem, st>>>(tm8, static_cast<float2 *>(G.y), G.ldy, (int)G.nch, P8);
+        if (cudaPeekAtLastError() != cudaSuccess) return -2;
+        *name = "decim8_c64";
+        ++*launches;
+        return k_begin;
+    }
     DecParams &P = *p.hp;
     P.k_begin = k_begin; P.N = G.nout; P.e = e; P.delta = (int)delta;
-    const int64_t span = G.nout - k_begin;
     const int64_t groups = ceil_div(G.nch, kDecRows);
     const int64_t R = 8;                                     // DecCfg<M>::R
     static const int wv = getenv("MRB_DEC_WAVES") ? atoi(getenv("MRB_DEC_WAVES")) : 4;

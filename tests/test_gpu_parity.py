@@ -457,6 +457,38 @@ def test_decimator_c64_kernel_shapes(M, ntaps, nch, tx, rng):
         assert any(k.startswith("decim_c64" if tx == np.complex64 else "decim_f32") for k in used), used
 
 
+@pytest.mark.parametrize("ntaps,nch", [(256, 300), (255, 129), (100, 512), (9, 160)])
+def test_decimator_m8_lane_per_channel_kernel(ntaps, nch, rng):
+    """k_decim8 (mrb_decim.cuh): 1//8 on complex64 with the taps as launch constants -- ragged tap and channel counts, chunk
+    lengths that leave every input deficit behind (both window alignments), tiles that end inside a step, state carry;
+    against the oracle and the generic kernel."""
+    import torch
+    h = rng.standard_normal(ntaps).astype(np.float32)
+    ratio = Fraction(1, 8)
+    n = 70000
+    x = rand_samples(rng, (nch, n), np.complex64)
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, ratio)
+    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=np.complex64)
+    g.set_kernel_policy(1)
+    o = mo.FIRFilter(h, ratio)
+    edges = [0, 30000, 30001, 30003, 50004, 50010, n]
+    rows = [0, 1, nch // 2, nch - 1]
+    used = set()
+    for a, b in zip(edges[:-1], edges[1:]):
+        yd = f.filt(xd[:, a:b])
+        yg = g.filt(xd[:, a:b])
+        w = o.filt(x[rows, a:b])
+        torch.cuda.synchronize()
+        y = yd.cpu().numpy()
+        assert y.shape == (nch, w.shape[1])
+        assert nerr(y[rows], w) <= 1e-5
+        assert nerr(yg.cpu().numpy(), y) <= 2e-6
+        assert states_equal(f, o)
+        used.add(f.last_kernel)
+    assert "decim8_c64" in used, used
+
+
 @pytest.mark.parametrize("th,tx", [(np.float32, np.float32), (np.float32, np.complex64), (np.float64, np.float64),
                                    (np.float64, np.complex128), (np.float64, np.complex64)])
 @pytest.mark.parametrize("M,ntaps,nch", [(8, 256, 40), (4, 77, 3), (16, 300, 1)])
