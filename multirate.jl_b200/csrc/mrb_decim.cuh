@@ -225,125 +225,195 @@ k_decim(const __grid_constant__ CUtensorMap tmx, void *__restrict__ yv, long lon
 // one channel (16 channels x 2 output blocks per warp) and computes 8 consecutive outputs from a 320-sample window read
 // ONCE with LDS.128 (two complex samples, [16 ch][16 samples] boxes with the 128-byte swizzle: conflict free), with
 //     acc[r] += h[8 (m - r) + q] * x[8 m + q]        r = 0..7 outputs, window position 8 m + q
-// fully unrolled: every tap is a compile-time offset into the kernel's parameter block, i.e. a constant-bank operand
-// fetched by the uniform datapath (LDCU) -- no tap registers, no tap loads on the LSU, no cross-lane reduction, 13 FFMA2
-// per shared-memory load.  The price is shared memory: the outputs in flight need their 8 new samples each (64 B per
-// output and channel), so an SM holds 4 warps x 32 lanes x 8 outputs = 64 KB of new samples per step, in a ring of three
-// 64 KB super-groups (512 samples x 16 channels) with one full and one empty mbarrier each: a step reads super-groups s
-// and s+1 while the producer warp fills s+2.  One CTA (4 consumer warps + producer) per SM; latency is hidden inside the
-// warp (8 independent accumulators, loads hoisted by the compiler over the static schedule).
+// unrolled over m and r: every tap sits at a fixed offset of the kernel's parameter block (constant bank; no tap table
+// in registers or shared memory, no tap loads on the LSU), there is no cross-lane reduction, and an FFMA2 is 83 % of
+// the instruction stream (13 per shared-memory load).  The price is shared memory: the outputs in flight need their 8 new
+// samples each (64 B per output and channel), so a step of 64 outputs x 16 channels holds 64 KB of new samples; the ring
+// is six 32 KB units (256 samples x 16 channels) with a full and an empty mbarrier each, filled by a producer warp that
+// runs up to three units ahead.  The 2112 FFMA2 of a lane's step are split over a QUARTET of warps by q-pair (each warp
+// reads its own quarter of the window); three helpers hand their partial sums to the first through shared memory (named
+// barriers).  One persistent CTA per SM (16 consumer warps + producer) walks the work items round robin.
+__device__ __forceinline__ void cfma_ordered(unsigned long long &acc, float t, unsigned long long x) {
+    unsigned long long tt;
+    asm("mov.b64 %0, {%1,%1};" : "=l"(tt) : "f"(t));
+    asm volatile("fma.rn.f32x2 %0, %2, %1, %0;" : "+l"(acc) : "l"(tt), "l"(x));
+}
+
 constexpr int kD8Ch = 16;               // channels per CTA
 constexpr int kD8Step = 64;             // outputs per channel and CTA step
 constexpr int kD8TQ = 33;               // tap slots per residue (T <= 256, one slot of slack for the alignment shift)
-constexpr int kD8SG = 65536;            // bytes per super-group: 512 samples x 16 channels x 8 B = 32 boxes of 2 KB
-constexpr int kD8Smem = 3 * kD8SG + 64;
+constexpr int kD8Unit = 32768;          // ring unit: 256 samples x 16 channels x 8 B = 16 boxes of 2 KB
+constexpr int kD8NU = 6;                // ring units: a step reads three, the producer runs up to three ahead
+constexpr int kD8Scratch = 4 * 3 * 2048;   // partial sums of the three helper warps of every (a, b) quartet
+constexpr int kD8Smem = kD8NU * kD8Unit + kD8Scratch + 128;
 
 struct alignas(16) Dec8Params {
     long long k_begin, N;      // this launch covers outputs [k_begin, N)
     long long e;               // x index of the first sample of output 0's padded window (even)
-    int KT, pad;               // outputs per tile (multiple of 64)
+    int KT;                    // outputs per work item (multiple of 64)
+    int tiles, items, pad;     // items = channel groups x tiles; item i = (group i / tiles, tile i % tiles)
     float hq[4][kD8TQ][2];     // hq[c][j][b] = padded hflip[8 j + 2 c + b]
 };
 
-__global__ void __launch_bounds__(160, 1)
+// One q-pair (window chunks 4 (m & 1) + C of every 16-sample box) of a lane's 8 outputs.  C is a RUN-TIME value: one copy of
+// the 528-FFMA2 body (10 KB) serves the four q-pairs, the 66 taps are fetched from the parameter block with a register
+// offset (LDC.64).  Measured alternatives: four compile-time copies (taps as LDCU / UR operands, 40 KB of code) miss the
+// 32 KB instruction cache -- 27.4 Gout/s straight-line in every warp, 30.7 with one copy per warp quartet, against 39.8.
+__device__ __forceinline__ void d8_body(const int C, unsigned long long (&acc)[8], const uint32_t (&base)[5], uint32_t sw, const Dec8Params &P) {
+    const uint32_t xe = ((uint32_t)C ^ sw) << 4;                     // chunk C of the lane's row (m even)
+    const uint32_t xo = ((uint32_t)(4 + C) ^ sw) << 4;               // chunk 4 + C (m odd)
+    // volatile asm keeps the issue order as written: loads run PF window positions ahead of their FFMA2s, every FFMA2 is
+    // followed by seven on other accumulators
+    constexpr int PF = 4;
+    unsigned long long xa[40], xb[40];
+    auto lds = [&](int m) {
+        // window position 8 m + 2 C (+1): group m / 8, box (m % 8) / 2, chunk 4 (m & 1) + C
+        const uint32_t ad = base[m >> 3] + (uint32_t)(((m & 7) >> 1) * 2048) + ((m & 1) ? xo : xe);
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xa[m]), "=l"(xb[m]) : "r"(ad) : "memory");
+    };
+#pragma unroll
+    for (int m = 0; m < PF; ++m) lds(m);
+#pragma unroll
+    for (int m = 0; m < 40; ++m) {
+        if (m + PF < 40) lds(m + PF);
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (m - r >= 0 && m - r < kD8TQ) cfma_ordered(acc[r], P.hq[C][m - r][0], xa[m]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (m - r >= 0 && m - r < kD8TQ) cfma_ordered(acc[r], P.hq[C][m - r][1], xb[m]);
+    }
+}
+
+// Persistent CTAs (one per SM) walk the work items round robin; the ring and its mbarrier phases run on across items (a
+// global unit counter), so the producer is already fetching the next item while the consumers finish this one.
+// Unit u of an item = samples [256 u, 256 u + 256) of its window; step s reads units 2s, 2s+1 (warps a = 0: window groups
+// 0..7 of the step) or 2s+1, 2s+2 (warps a = 1: groups 4..11).  Every unit collects four "empty" arrivals: two from the
+// a = 0 warps, two from the a = 1 warps; the item's first unit (not read by a = 1) and last unit (not read by a = 0) get
+// the missing two as courtesy arrivals.
+__global__ void __launch_bounds__(544, 1)
 k_decim8(const __grid_constant__ CUtensorMap tmx, float2 *__restrict__ y, long long ldy, int nch,
          const __grid_constant__ Dec8Params P) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t ring = smem_u32(smem), full = ring + 3 * kD8SG, empty = full + 24;
-    const int ch0 = blockIdx.y * kD8Ch;
-    const long long k0 = P.k_begin + (long long)blockIdx.x * P.KT;
-    const int ntile = (int)min((long long)P.KT, P.N - k0);
-    const int nsteps = (ntile + kD8Step - 1) / kD8Step;
-    const long long x0 = P.e + k0 * 8;                               // x index of the tile's first sample (even, >= 0)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler: the tap offsets become uniform
+    const uint32_t ring = smem_u32(smem), scratch = ring + kD8NU * kD8Unit, full = scratch + kD8Scratch, empty = full + 8 * kD8NU;
 
     if (tid == 0) {
         if (ring & 1023u) __trap();
-        for (int i = 0; i < 3; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 4); }
+        for (int i = 0; i < kD8NU; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
     }
     __syncthreads();
 
-    if (warp == 4) {
-        // ---- producer: super-group sg = samples [512 sg, 512 sg + 512) of the tile; the last one is read only in its
-        // first 256 samples (the window tail of the last step)
+    if (warp == 16) {
         if (lane == 0) {
-            for (int sg = 0; sg <= nsteps; ++sg) {
-                const int slot = sg % 3;
-                if (sg >= 3) mbar_wait(empty + 8 * slot, (uint32_t)((sg / 3 - 1) & 1));
-                const int nbox = sg == nsteps ? 16 : 32;
-                mbar_expect_tx(full + 8 * slot, (uint32_t)(nbox * 2048));
-                for (int bx = 0; bx < nbox; ++bx)
-                    tma_load_2d(ring + (uint32_t)(slot * kD8SG + bx * 2048), &tmx, (int)((x0 + sg * 512 + bx * 16) * 2), ch0,
-                                full + 8 * slot);
+            unsigned U = 0;                                          // units issued so far (all items)
+            for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
+                const int ch0 = (item / P.tiles) * kD8Ch;
+                const long long k0 = P.k_begin + (long long)(item % P.tiles) * P.KT;
+                const int ntile = (int)min((long long)P.KT, P.N - k0);
+                const int nsteps = (ntile + kD8Step - 1) / kD8Step;
+                const long long x0 = P.e + k0 * 8;                   // x index of the item's first sample (even, >= 0)
+                for (int u = 0; u <= 2 * nsteps; ++u, ++U) {
+                    const unsigned slot = U % kD8NU;
+                    if (U >= kD8NU) mbar_wait(empty + 8 * slot, (U / kD8NU - 1) & 1u);
+                    mbar_expect_tx(full + 8 * slot, kD8Unit);
+                    for (int bx = 0; bx < 16; ++bx)
+                        tma_load_2d(ring + slot * kD8Unit + (uint32_t)(bx * 2048), &tmx, (int)((x0 + u * 256 + bx * 16) * 2), ch0,
+                                    full + 8 * slot);
+                }
             }
         }
         return;
     }
 
     // ---- consumers: warp (a, b), lane half hb -> outputs 8 o .. 8 o + 7 of the step, o = 4 a + 2 hb + b; the lane's
-    // window is the five 64-sample groups o .. o + 4 of the step (8 groups per super-group)
-    const int chl = lane & 15, hb = lane >> 4;
-    const int o = 4 * (warp >> 1) + 2 * hb + (warp & 1);
-    const int c_glob = ch0 + chl;
-    float2 *yrow = y + (long long)c_glob * ldy;
-
-    mbar_wait(full, 0u);
-    for (int s = 0; s < nsteps; ++s) {
-        mbar_wait(full + 8 * (uint32_t)((s + 1) % 3), (uint32_t)(((s + 1) / 3) & 1));
-        uint32_t base[5];
+    // window is the five 64-sample groups o .. o + 4 of the step (4 groups per unit)
+    // Four warps share every (a, b): warp c of the quartet takes q-pair c (its own 40 of the 160 window loads) and the three
+    // helpers hand their partial sums to the first through shared memory -- sixteen consumer warps, four per scheduler
+    // (measured: 4 warps 37.9, 8 warps 39.6 Gout/s: the FMA pipe wants more than two warps to pick from).
+    const int chl = lane & 15, hb = lane >> 4, c = warp & 3, pair = warp >> 2, a = pair >> 1;
+    const int o = 4 * a + 2 * hb + (pair & 1);     // (c = warp & 3: a scheduler's four warps run ONE q-pair's code)
+    unsigned gs = 0;                                                 // steps done so far (all items)
+    const uint32_t lanerow = (uint32_t)(chl * 128), sw = (uint32_t)(chl & 7);
+    unsigned U0 = 0;                                                 // unit counter at the start of the item
+    for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
+        const int c_glob = (item / P.tiles) * kD8Ch + chl;
+        const long long k0 = P.k_begin + (long long)(item % P.tiles) * P.KT;
+        const int ntile = (int)min((long long)P.KT, P.N - k0);
+        const int nsteps = (ntile + kD8Step - 1) / kD8Step;
+        float2 *yrow = y + (long long)c_glob * ldy;
+        if (a == 1 && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty + 8 * (U0 % kD8NU)) : "memory");
+        for (int s = 0; s < nsteps; ++s) {
+            const unsigned ua = U0 + 2 * s + a;                      // first of the two units this warp reads
+            mbar_wait(full + 8 * (ua % kD8NU), (ua / kD8NU) & 1u);
+            mbar_wait(full + 8 * ((ua + 1) % kD8NU), ((ua + 1) / kD8NU) & 1u);
+            uint32_t base[5];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int gg = o + i;
-            base[i] = ring + (uint32_t)(((s + (gg >> 3)) % 3) * kD8SG + (gg & 7) * 8192);
-        }
-        unsigned long long acc[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = 0ull;
-        // the q-pair loop is NOT unrolled: 2112 FFMA2 of straight-line code (40 KB) miss the 32 KB instruction cache (18 % of
-        // the issue slots went to "no instruction"); per q-pair the 66 taps are fetched with a uniform base offset
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            const uint32_t xe = (uint32_t)(chl * 128 + ((c ^ (chl & 7)) << 4));           // chunk c of the lane's row (m even)
-            const uint32_t xo = (uint32_t)(chl * 128 + (((4 + c) ^ (chl & 7)) << 4));     // chunk 4 + c (m odd)
-#pragma unroll
-            for (int m = 0; m < 40; ++m) {
-                // window position 8 m + 2 c (+1): group m / 8, box (m % 8) / 2, chunk 4 (m & 1) + c
-                const uint32_t ad = base[m >> 3] + (uint32_t)(((m & 7) >> 1) * 2048) + ((m & 1) ? xo : xe);
-                unsigned long long xa, xb;
-                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xa), "=l"(xb) : "r"(ad) : "memory");
-                // eight independent accumulators in a row, then the second sample: no back-to-back dependent FFMA2
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (m - r >= 0 && m - r < kD8TQ) cfma(acc[r], P.hq[c][m - r][0], xa);
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (m - r >= 0 && m - r < kD8TQ) cfma(acc[r], P.hq[c][m - r][1], xb);
+            for (int i = 0; i < 5; ++i) {
+                const int gg = o + i;
+                base[i] = ring + ((U0 + 2 * s + (gg >> 2)) % kD8NU) * kD8Unit + (uint32_t)((gg & 3) * 8192) + lanerow;
             }
-        }
-        // ---- 8 consecutive outputs of one channel: 64 contiguous bytes
-        const long long k = k0 + (long long)s * kD8Step + 8 * o;
-        if (c_glob < nch) {
-            if (k + 8 <= P.N && ((reinterpret_cast<uintptr_t>(yrow + k) & 15) == 0)) {
+            unsigned long long acc[8];
 #pragma unroll
-                for (int r = 0; r < 8; r += 2) {
-                    float4 v;
-                    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(acc[r]));
-                    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(acc[r + 1]));
-                    *reinterpret_cast<float4 *>(yrow + k + r) = v;
-                }
-            } else {
+            for (int r = 0; r < 8; ++r) acc[r] = 0ull;
+            d8_body(c, acc, base, sw, P);
+            // ---- this warp is done with its two units
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty + 8 * (ua % kD8NU)) : "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty + 8 * ((ua + 1) % kD8NU)) : "memory");
+            }
+            // ---- the quartet's partial sums meet: [pair][helper][r][lane]; named barriers 1 + 2 pair (data ready) and
+            // 2 + 2 pair (scratch free again)
+            const uint32_t sc = scratch + (uint32_t)(pair * 3 * 2048 + lane * 8);
+            if (c != 0) {
+                if (gs) asm volatile("bar.sync %0, 128;" ::"r"(2 + 2 * pair) : "memory");
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    asm volatile("st.shared.b64 [%0], %1;" ::"r"(sc + (uint32_t)((c - 1) * 2048 + r * 256)), "l"(acc[r]) : "memory");
+                asm volatile("bar.arrive %0, 128;" ::"r"(1 + 2 * pair) : "memory");
+                ++gs;
+                continue;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * pair) : "memory");
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    float2 v;
-                    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(acc[r]));
-                    if (k + r < P.N) yrow[k + r] = v;
+                    unsigned long long v;
+                    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(sc + (uint32_t)(w * 2048 + r * 256)) : "memory");
+                    acc[r] = cadd(acc[r], v);
+                }
+            }
+            asm volatile("bar.arrive %0, 128;" ::"r"(2 + 2 * pair) : "memory");
+            ++gs;
+            // ---- 8 consecutive outputs of one channel: 64 contiguous bytes
+            const long long k = k0 + (long long)s * kD8Step + 8 * o;
+            if (c_glob < nch) {
+                if (k + 8 <= P.N && ((reinterpret_cast<uintptr_t>(yrow + k) & 15) == 0)) {
+#pragma unroll
+                    for (int r = 0; r < 8; r += 2) {
+                        float4 v;
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(acc[r]));
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(acc[r + 1]));
+                        *reinterpret_cast<float4 *>(yrow + k + r) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        float2 v;
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(acc[r]));
+                        if (k + r < P.N) yrow[k + r] = v;
+                    }
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty + 8 * (uint32_t)(s % 3)) : "memory");
+        if (a == 0 && lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty + 8 * ((U0 + 2 * nsteps) % kD8NU)) : "memory");
+        U0 += 2 * nsteps + 1;
     }
 }
 
@@ -498,16 +568,19 @@ static inline int64_t decim_try_launch(DecPlan &p, const GenParams &G, cudaStrea
         P8.k_begin = k_begin; P8.N = G.nout; P8.e = e;
         memcpy(P8.hq, p.h8[delta], sizeof(P8.hq));
         const int64_t groups8 = ceil_div(G.nch, kD8Ch);
-        // tiles per channel group: whole waves of one CTA per SM, each tile pays about 1.5 steps of ring fill
-        int64_t best_t = 1;
+        // work items of `ts` steps, walked round robin by one persistent CTA per SM: pick the item length with the shortest
+        // makespan (an item boundary costs a fraction of a step: the producer is already ahead)
+        const int64_t total_steps = ceil_div(span, kD8Step);
+        int64_t best_ts = 1;
         double best = 1e300;
-        for (int64_t t = 1; t <= std::min<int64_t>(span / kD8Step, 256); ++t) {
-            const int64_t steps = ceil_div(ceil_div(span, t), kD8Step);
-            const double cost = (double)ceil_div(t * groups8, p.num_sms) * ((double)steps + 1.5);
-            if (cost < best) { best = cost; best_t = t; }
+        for (int64_t ts = 2; ts <= std::min<int64_t>(total_steps, 64); ++ts) {
+            const int64_t items = groups8 * ceil_div(total_steps, ts);
+            const double cost = (double)ceil_div(items, p.num_sms) * ((double)ts + 0.3);
+            if (cost < best) { best = cost; best_ts = ts; }
         }
-        P8.KT = (int)(ceil_div(ceil_div(span, best_t), kD8Step) * kD8Step);
+        P8.KT = (int)(best_ts * kD8Step);
         const int64_t tiles8 = ceil_div(span, P8.KT);
+        P8.tiles = (int)tiles8; P8.items = (int)(tiles8 * groups8);
         CUtensorMap tm8;
         cuuint64_t dims[2] = {(cuuint64_t)(2 * G.n_in), (cuuint64_t)G.nch};
         cuuint64_t strides[1] = {(cuuint64_t)G.ldx * 8};
@@ -517,7 +590,7 @@ static inline int64_t decim_try_launch(DecPlan &p, const GenParams &G, cudaStrea
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             MRB_DEC_SKIP("x tensor map");
-        k_decim8<<<dim3((unsigned)tiles8, (unsigned)groups8), 160, kD8Smem, st>>>(tm8, static_cast<float2 *>(G.y), G.ldy, (int)G.nch, P8);
+        k_decim8<<<(unsigned)std::min<int64_t>(P8.items, p.num_sms), 544, kD8Smem, st>>>(tm8, static_cast<float2 *>(G.y), G.ldy, (int)G.nch, P8);
         if (cudaPeekAtLastError() != cudaSuccess) return -2;
         *name = "decim8_c64";
         ++*launches;
