@@ -592,6 +592,8 @@ def test_table_kernel_arbitrary_farrow(tx, polyorder, rate, nch, rng):
     # (float64 below rate 0.5: a step's windows do not fit the shared-memory ring -> generic kernel, by design)
     # float32: the tensor-core kernel (mrb_mma.cuh); float64 / complex64: the table kernel
     assert any(k.startswith(("table_", "mma_")) for k in used) or (tx != np.float32 and rate < 0.5), used
+    if tx == np.float64 and rate >= 0.5:
+        assert "table_f64_dmma" in used, used                      # the FP64 tensor-core variant (mma.sync m8n8k4)
 
 
 @pytest.mark.parametrize("case", ["rational", "decimator", "interpolator", "standard", "arbitrary", "farrow"])
