@@ -128,7 +128,7 @@ constexpr int kTabWPG = 1;
 // instruction and 16 loaded bytes per 256 FMAs instead of per 32 / 64: the kernel leaves the LSU wall (DFMA and DMMA peak at
 // the same 37 TFLOP/s on this part, profiles/r2_dfma_probe.txt).  TB = 4 (one k-slice) in this variant.
 template <int K, int TB, int CH, int DM = 0>
-__global__ void __launch_bounds__(DM ? DM * 32 : 128 * kTabWPG, CH == 1 ? 3 : 1)
+__global__ void __launch_bounds__(DM == 8 ? 288 : DM ? DM * 32 : 128 * kTabWPG, CH == 1 ? 3 : 1)
 k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
             const typename TabCfg<K>::Tap *__restrict__ rows, const int32_t *__restrict__ astart,
             const __grid_constant__ TabParams P) {
@@ -152,6 +152,10 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     // barrier is a quarter of the SM idle) -- thread 0 makes sure the previous step's store has left its buffer BEFORE the
     // barrier, issues this step's store after it and does not wait for it
     constexpr bool DB = DM != 0;
+    // PW (DM = 8): a ninth warp takes thread 0's per-step duties (output store, ring refill, next tap rows) and the CTA barrier
+    // goes: consumers arrive on done[s & 1] when their part of the step is staged, the producer signals free[b] when the store
+    // that read staging buffer b has finished -- the consumer warps run from step to step without meeting
+    constexpr bool PW = DM == 8;
     constexpr int STG_BYTES = ROWS * kTabStep * ES;
     unsigned char *rows_s = out_buf + (DB ? 2 : 1) * STG_BYTES;
     int *ast_s = reinterpret_cast<int *>(rows_s + 2 * row_bytes);    // [2][32]
@@ -163,6 +167,7 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     const int ch0 = blockIdx.x * ROWS;
     const uint32_t in_base = smem_u32(smem), obase = smem_u32(out_buf), bar_base = smem_u32(bars);
     const uint32_t rbar_base = bar_base + 8 * NB;                    // two mbarriers for the staged rows
+    const uint32_t done_base = rbar_base + 16, free_base = done_base + 16;   // PW: two "step staged", two "staging free"
     const uint32_t rowpart = ((uint32_t)lane * 128u) ^ (((uint32_t)lane & 7u) << 4);   // SWIZZLE_128B
     auto stage_rows = [&](long long kstep, int slot) {               // thread 0 only
         const uint32_t bar = rbar_base + 8 * slot;
@@ -181,6 +186,10 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     if (tid == 0) {
         if (in_base & 1023u) __trap();
         for (int i = 0; i < NB + 2; ++i) mbar_init(bar_base + 8 * i, 1);
+        if constexpr (PW) {
+            mbar_init(done_base, DM); mbar_init(done_base + 8, DM);
+            mbar_init(free_base, 1); mbar_init(free_base + 8, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmx) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmy) : "memory");
@@ -196,6 +205,39 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
     int j_issued = min(NB, jlast + 1), i_slot = j_issued % NB;
     int j_waited = 0, w_slot = 0;
     uint32_t w_par = 0;
+
+    if constexpr (PW) {
+        if (warp == DM) {                                            // ---- producer warp
+            if (lane == 0) {
+                for (int s = 0; s < nsteps; ++s) {
+                    const long long ks = k0 + (long long)s * kTabStep;
+                    const int rslot = s & 1;
+                    mbar_wait(done_base + 8 * rslot, (uint32_t)((s >> 1) & 1));       // every warp has staged step s
+                    constexpr int NST = kTabStep * ES / 128;
+                    for (int b = 0; b < NST; ++b)
+                        tma_store_2d(&tmy, (int)(P.y0 + ks) + b * C::BOXE, ch0, obase + (uint32_t)(rslot * STG_BYTES + b * ROWS * 128));
+                    tma_commit();
+                    int jtarget = jlast;
+                    if (s + 1 < nsteps) {                            // the next step's first window start is already in shared memory
+                        mbar_wait(rbar_base + 8 * (rslot ^ 1), (uint32_t)(((s + 1) >> 1) & 1));
+                        jtarget = min((ast_s[(rslot ^ 1) * kTabStep] - xbase) / C::BOXE + NB - 1, jlast);
+                    }
+                    for (int jj = j_issued; jj <= jtarget; ++jj) {
+                        const uint32_t bar = bar_base + 8 * i_slot;
+                        mbar_expect_tx(bar, BOX_BYTES);
+                        tma_load_2d(in_base + (uint32_t)(i_slot * BOX_BYTES), &tmx, xbase + jj * C::BOXE, ch0, bar);
+                        if (++i_slot == NB) i_slot = 0;
+                    }
+                    if (jtarget >= j_issued) j_issued = jtarget + 1;
+                    if (s + 2 < nsteps) stage_rows(ks + 2 * kTabStep, rslot);
+                    tma_wait_read<1>();                              // the store of step s - 1 has left its buffer
+                    if (s >= 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(free_base + 8 * (uint32_t)(rslot ^ 1)) : "memory");
+                }
+                tma_wait_read<0>();
+            }
+            return;
+        }
+    }
 
     for (int s = 0; s < nsteps; ++s) {
         const long long ks = k0 + (long long)s * kTabStep;
@@ -256,6 +298,9 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
                 }
             }
             // stage: lane holds channel 8 c + rr, outputs 2 kq and 2 kq + 1 of the group
+            if constexpr (PW) {
+                if (s >= 2) mbar_wait(free_base + 8 * (uint32_t)(s & 1), (uint32_t)(((s >> 1) - 1) & 1));   // store s - 2 is done
+            }
             const uint32_t byte = (uint32_t)(grp * kTabGroup + 2 * kq) * 8u;
 #pragma unroll
             for (int c = 0; c < CB; ++c) {
@@ -396,6 +441,11 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
 
         // ---- the step's outputs leave; boxes before the next step's first window are refilled
         fence_async_smem();
+        if constexpr (PW) {
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(done_base + 8 * (uint32_t)(s & 1)) : "memory");
+            continue;
+        }
         if constexpr (DB) {
             if (tid == 0) tma_wait_read<0>();              // the previous step's store has left the other staging buffer
             __syncthreads();
@@ -446,7 +496,7 @@ k_table_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUt
         }
         __syncthreads();
     }
-    if (DB && tid == 0) tma_wait_read<0>();               // the last store still reads its staging buffer
+    if (DB && !PW && tid == 0) tma_wait_read<0>();        // the last store still reads its staging buffer (PW: the producer waits)
     for (; j_waited < j_issued; ++j_waited) {             // every issued load must have landed before exit (DB: thread 0 knows)
         mbar_wait(bar_base + 8 * w_slot, w_par);
         if (++w_slot == NB) { w_slot = 0; w_par ^= 1u; }
@@ -490,7 +540,7 @@ static inline void table_release(TabPlan &p) {
 
 static inline int table_smem(const TabPlan &p) {
     return p.NB * p.ch * kTabRows * 128 + (p.dm ? 2 : 1) * p.ch * kTabRows * kTabStep * p.es + 2 * kTabStep * p.rowlen * p.ts + 2 * kTabStep * 4 +
-           8 * (p.NB + 2);
+           8 * (p.NB + 6);
 }
 
 // kind/tx/ty are the mrb.h enums (4 arbitrary, 5 farrow ; 0 = float32, 1 = float64, 2 = complex64)
@@ -645,7 +695,7 @@ static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams 
     if (p.dm == 4) {
         k_table_fir<TAB_F64, 4, 2, 4><<<grid, 128, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
     } else if (p.dm == 8) {
-        k_table_fir<TAB_F64, 4, 2, 8><<<grid, 256, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
+        k_table_fir<TAB_F64, 4, 2, 8><<<grid, 288, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
     } else if (p.ch == 2) {
         if (red) k_table_fir<TAB_F64, 22, 2><<<grid, 128 * kTabWPG, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
         else k_table_fir<TAB_F64, 24, 2><<<grid, 128 * kTabWPG, smem, st>>>(tmx, tmy, (const double *)rw.d_rows, rw.d_astart, P);
