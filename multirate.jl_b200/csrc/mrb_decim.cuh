@@ -251,8 +251,8 @@ struct alignas(16) Dec8Params {
     long long k_begin, N;      // this launch covers outputs [k_begin, N)
     long long e;               // x index of the first sample of output 0's padded window (even)
     int KT;                    // outputs per work item (multiple of 64)
-    int tiles, items, pad;     // items = channel groups x tiles; item i = (group i / tiles, tile i % tiles)
-    float hq[4][kD8TQ][2];     // hq[c][j][b] = padded hflip[8 j + 2 c + b]
+    int tiles, items, pad[3];  // items = channel groups x tiles; item i = (group i / tiles, tile i % tiles)
+    float hq[4][kD8TQ + 1][2]; // hq[c][j][b] = padded hflip[8 j + 2 c + b]; rows of 34 slots at a 16-byte aligned offset (LDCU.128)
 };
 
 // One q-pair (window chunks 4 (m & 1) + C of every 16-sample box) of a lane's 8 outputs.  C is a RUN-TIME value: one copy of
@@ -274,11 +274,14 @@ __device__ __forceinline__ void d8_body(const int C, unsigned long long (&acc)[8
     // the taps of this q-pair, declared warp-uniform to the compiler (a shuffle from lane 0 of a value every lane holds):
     // FFMA2 then takes them from uniform registers -- with a vector-register scalar the FFMA2 reads five registers and
     // measured 70 % of its issue rate
-    float t0[kD8TQ], t1[kD8TQ];
+    float t0[kD8TQ + 1], t1[kD8TQ + 1];
 #pragma unroll
-    for (int j = 0; j < kD8TQ; ++j) {
-        t0[j] = __shfl_sync(0xffffffffu, P.hq[C][j][0], 0);
-        t1[j] = __shfl_sync(0xffffffffu, P.hq[C][j][1], 0);
+    for (int j = 0; j < kD8TQ + 1; j += 2) {                         // two slots = 16 bytes per fetch
+        const float4 v = *reinterpret_cast<const float4 *>(&P.hq[C][j][0]);
+        t0[j] = __shfl_sync(0xffffffffu, v.x, 0);
+        t1[j] = __shfl_sync(0xffffffffu, v.y, 0);
+        t0[j + 1] = __shfl_sync(0xffffffffu, v.z, 0);
+        t1[j + 1] = __shfl_sync(0xffffffffu, v.w, 0);
     }
 #pragma unroll
     for (int m = 0; m < PF; ++m) lds(m);
@@ -441,7 +444,7 @@ struct DecPlan {
     // k_decim8 (M = 8, complex64): the padded taps for both alignments, copied into every launch's parameter block
     bool d8 = false;
     Dec8Params *hp8 = nullptr;
-    float h8[2][4][kD8TQ][2];
+    float h8[2][4][kD8TQ + 1][2];
 };
 
 // hq tables of k_decim8 from the flipped taps (bank[i] multiplies window sample i)
