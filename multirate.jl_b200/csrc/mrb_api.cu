@@ -64,6 +64,7 @@ struct SchedSlot {            // device copy of one table-schedule sub-chunk
     int64_t *d_n = nullptr;
     int32_t *d_phi = nullptr;
     double *d_a = nullptr;
+    uint64_t tag = 0;         // (call serial, slice) the slot holds: the channel blocks of one mrb_filt_host call share it
 };
 
 // Host storage of one replayed schedule: (n, phi, alpha | phase) per output.  PINNED on device-bound handles, so the
@@ -182,6 +183,7 @@ struct mrb_filter {
     DecPlan decim;                     // fast path for complex64 decimators (mrb_decim.cuh)
     TabPlan table;                     // fast path for arbitrary / farrow on real samples (mrb_table.cuh)
     MmaPlan mma;                       // tensor-core path for float32 samples (mrb_mma.cuh)
+    uint64_t serial = 0;               // filt calls so far (tags what the table contexts hold)
     int policy = 0;
     int host_block_mib = 0, host_streams_n = 0;   // mrb_set_host_pipeline; 0 = MRB_HOST_BLOCK_MIB / MRB_HOST_STREAMS / default
     int num_sms = 148;
@@ -1051,11 +1053,16 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 const int64_t cnt = std::min(kSchedChunk, N - k0);
                 SchedSlot &s = tc.slot[si];
                 // uploaded straight from the pinned store (stream order keeps a slot's previous readers ahead of this write)
-                CU(cudaMemcpyAsync(s.d_n, vn + k0, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-                CU(cudaMemcpyAsync(s.d_a, va + k0, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
-                if (f->kind == MRB_ARBITRARY)
-                    CU(cudaMemcpyAsync(s.d_phi, vphi + k0, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-                if (k0 + cnt >= N) { CU(cudaEventRecord(store.ev, st)); store.pending = true; }   // the store is free again after this
+                // (a later channel block of the same host call on this stream finds slice, tap rows and tiles in place)
+                const uint64_t tag = f->serial * 65536 + (uint64_t)(k0 / kSchedChunk) + 1;
+                if (s.tag != tag) {
+                    CU(cudaMemcpyAsync(s.d_n, vn + k0, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+                    CU(cudaMemcpyAsync(s.d_a, va + k0, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+                    if (f->kind == MRB_ARBITRARY)
+                        CU(cudaMemcpyAsync(s.d_phi, vphi + k0, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                    s.tag = tag;
+                    if (k0 + cnt >= N) { CU(cudaEventRecord(store.ev, st)); store.pending = true; }   // the store is free again after this
+                }
                 P.sn = s.d_n; P.k_base = k0; P.nout = cnt;
                 P.sphi = s.d_phi; P.salpha = s.d_a;
                 cudaStream_t hs = st;                          // stream of the slice's head
@@ -1072,7 +1079,7 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                         MmaSched S{};
                         S.mode = f->kind == MRB_FARROW ? 1 : 0; S.sn = s.d_n; S.sphi = s.d_phi; S.sa = s.d_a;
                         kb = mma_try_launch(f->mma, tc.mrows, P, S, f->polyorder + 1, f->d_bank, f->d_dbank, f->d_pnfb, k0, cnt, gs32, st,
-                                            &f->last_kernel, &f->launches);
+                                            &f->last_kernel, &f->launches, tag);
                         if (kb == -2) return fail(MRB_ERR_CUDA, "tensor-core launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                     }
                     int64_t gspan = 0;                         // widest spread of window starts inside a group of 8 outputs
@@ -1081,7 +1088,7 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                             gspan = std::max(gspan, vn[k0 + std::min(g0 + kTabGroup, cnt) - 1] - vn[k0 + g0]);
                     if (kb == -1) kb = table_try_launch(f->table, tc.rows, P, f->kind, f->polyorder + 1, f->th == MRB_F32, f->d_bank,
                                                         f->d_dbank, f->d_pnfb, f->rate, k0, cnt, head, gspan, st, &f->last_kernel,
-                                                        &f->launches);
+                                                        &f->launches, tag);
                     if (kb == -2) return fail(MRB_ERR_CUDA, "table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                     if (kb == 0) continue;
                     if (kb > 0) {                              // the generic kernel computes the slice's head
@@ -1143,6 +1150,7 @@ extern "C" int32_t mrb_filt(mrb_filter *f, const void *x, int64_t ldx, int64_t n
     mrb_state end;
     int32_t rc = check_filt_args(f, x, ldx, n_in, y, ldy, cap, &N, &end);
     if (rc) return rc;
+    ++f->serial;
     DeviceGuard guard(f->device);
     rc = order_after_last(f, (cudaStream_t)stream);
     if (rc) return rc;
@@ -1172,13 +1180,17 @@ extern "C" int32_t mrb_filt_host(mrb_filter *f, const void *x, int64_t ldx, int6
     mrb_state end;
     int32_t rc = check_filt_args(f, x, ldx, n_in, y, ldy, cap, &N, &end);
     if (rc) return rc;
+    ++f->serial;
     DeviceGuard guard(f->device);
     const size_t es = dsize(f->tx), eo = dsize(f->ty);
     // channel blocks of ~MRB_HOST_BLOCK_MIB (64) MiB of input, pipelined over MRB_HOST_STREAMS (1..4, default 2) streams
     // (measured: 16..256 MiB x 2..4 streams all land on the same 86 GB/s full-duplex PCIe limit)
-    static const int env_mib = getenv("MRB_HOST_BLOCK_MIB") ? std::max(1, atoi(getenv("MRB_HOST_BLOCK_MIB"))) : 64;
+    // Default block: 64 MiB, but at least ~16 blocks per call -- the first block's upload and the last block's download have
+    // nothing to overlap with, which costs 1/(blocks) of the call (a 0.25 GiB call in four blocks ran at 64 % of the copy ceiling)
+    static const int env_mib = getenv("MRB_HOST_BLOCK_MIB") ? std::max(1, atoi(getenv("MRB_HOST_BLOCK_MIB"))) : 0;
     static const int env_nst = getenv("MRB_HOST_STREAMS") ? std::min(kMaxHostStreams, std::max(1, atoi(getenv("MRB_HOST_STREAMS")))) : 2;
-    const int blk_mib = f->host_block_mib > 0 ? f->host_block_mib : env_mib;
+    const int64_t total_mib = (int64_t)(((size_t)f->nch * (size_t)std::max<int64_t>(n_in, 1) * es) >> 20);
+    const int blk_mib = f->host_block_mib > 0 ? f->host_block_mib : env_mib > 0 ? env_mib : (int)std::min<int64_t>(64, std::max<int64_t>(8, total_mib / 16));
     const int nst = f->host_streams_n > 0 ? f->host_streams_n : env_nst;
     int64_t cb = std::max<int64_t>(1, (int64_t)(((size_t)blk_mib << 20) / std::max<size_t>(1, (size_t)n_in * es)));
     cb = std::min(cb, f->nch);

@@ -551,6 +551,7 @@ struct MmaRows {                       // per pipeline stream (TableCtx): the ta
     int32_t *d_gstart = nullptr;
     int64_t cap_tiles = 0, cap_groups = 0;
     int64_t tile_bytes = 0;
+    uint64_t tag = 0;                  // (call serial, slice) the tiles were built for: 0 = none
 };
 
 static inline void mmarows_release(MmaRows &r) {
@@ -605,7 +606,7 @@ static inline cudaError_t mma_reserve(MmaRows &r, int64_t ntiles, int64_t groups
 // (chunk head included).  Returns 0 (the first output covered), -1 when not covered, -2 on a CUDA error.
 static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G, const MmaSched &S, int P1,
                                      const void *d_pfb, const void *d_dpfb, const double *d_pnfb, int64_t y0, int64_t cnt,
-                                     int64_t max_group_span, cudaStream_t st, const char **name, int64_t *launches) {
+                                     int64_t max_group_span, cudaStream_t st, const char **name, int64_t *launches, uint64_t tag = 0) {
     static const bool trace = getenv("MRB_TRACE") != nullptr;
 #define MRB_MMA_SKIP(why) do { if (trace) fprintf(stderr, "[mrb] tensor-core kernel not used: %s\n", why); return -1; } while (0)
     if (!p.ok) MRB_MMA_SKIP("configuration not covered");
@@ -639,7 +640,11 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     }
     const int64_t ntiles = std::min(period, groups);
     const bool resident = S.mode == 2 && period <= nwb;
-    if (mma_reserve(rw, ntiles, groups, tile_bytes) != cudaSuccess) return -2;
+    {
+        const float *before = rw.d_tiles;
+        if (mma_reserve(rw, ntiles, groups, tile_bytes) != cudaSuccess) return -2;
+        if (rw.d_tiles != before) rw.tag = 0;
+    }
 
     MmaParams P{};
     static long long *d_prof = nullptr;
@@ -686,8 +691,11 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         MRB_MMA_SKIP("y tensor map");
 #undef MRB_MMA_SKIP
-    {   // pre-pass (launched only now: all host-side preparation is done, the two kernels go out back to back): one warp
-        // per tile row (rows past the last output are zero) and one thread per group for its window start
+    if (tag == 0 || rw.tag != tag) {
+        // pre-pass (launched only now: all host-side preparation is done, the two kernels go out back to back): one warp
+        // per tile row (rows past the last output are zero) and one thread per group for its window start.  Skipped when
+        // an earlier channel block of the same call already built this slice's tiles on this stream.
+        rw.tag = tag;
         const int64_t nrows = ntiles * GG;
         const unsigned gb = (unsigned)std::max(ceil_div(nrows, 8), ceil_div(groups, 256));
         k_mma_tiles<GG><<<gb, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, KB, S, G.H,

@@ -513,6 +513,7 @@ struct TabRows {
     int32_t *d_astart = nullptr;
     int64_t cap = 0;                   // outputs the two buffers hold
     int64_t row_bytes = 0;             // rowlen * tap bytes the buffers were sized for
+    uint64_t tag = 0;                  // (call serial, slice) the rows were built for: 0 = none
 };
 
 static inline void tabrows_release(TabRows &r) {
@@ -636,7 +637,8 @@ static inline cudaError_t table_reserve(const TabPlan &p, TabRows &r, int64_t no
 // (the caller computes the slice's outputs before it with the generic kernel), -1 when not covered, -2 on error.
 static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams &G, int kind, int P1, int tap_is_f32,
                                        const void *d_pfb, const void *d_dpfb, const double *d_pnfb, double rate, int64_t y0, int64_t cnt,
-                                       int64_t head, int64_t max_group_span, cudaStream_t st, const char **name, int64_t *launches) {
+                                       int64_t head, int64_t max_group_span, cudaStream_t st, const char **name, int64_t *launches,
+                                       uint64_t tag = 0) {
     static const bool trace = getenv("MRB_TRACE") != nullptr;
 #define MRB_TAB_SKIP(why) do { if (trace) fprintf(stderr, "[mrb] table kernel not used: %s\n", why); return -1; } while (0)
     if (!p.ok) MRB_TAB_SKIP("configuration not covered");
@@ -651,9 +653,16 @@ static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams 
     }
     const int64_t k_begin = (head + kTabStep - 1) / kTabStep * kTabStep;
     if (cnt - k_begin < 4 * kTabStep) MRB_TAB_SKIP("slice too short");
-    if (table_reserve(p, rw, cnt) != cudaSuccess) return -2;
+    {
+        const void *before = rw.d_rows;
+        if (table_reserve(p, rw, cnt) != cudaSuccess) return -2;
+        if (rw.d_rows != before) rw.tag = 0;
+    }
 
-    {   // pre-pass: rows + aligned starts for the whole slice (the head rows are not used)
+    if (tag == 0 || rw.tag != tag) {
+        // pre-pass: rows + aligned starts for the whole slice (the head rows are not used); skipped when an earlier channel
+        // block of the same call already built them on this stream
+        rw.tag = tag;
         const unsigned g = (unsigned)ceil_div(cnt, 8);               // one warp per row
         if (p.K == TAB_F64)
             k_table_rows<double><<<g, 256, 0, st>>>((const double *)d_pfb, (const double *)d_dpfb, d_pnfb, P1, p.T, p.rowlen,
