@@ -457,6 +457,38 @@ def test_decimator_c64_kernel_shapes(M, ntaps, nch, tx, rng):
         assert any(k.startswith("decim_c64" if tx == np.complex64 else "decim_f32") for k in used), used
 
 
+@pytest.mark.parametrize("case", ["decim8", "f64_arbitrary_dmma", "f64_farrow_dmma"])
+def test_mbarrier_pipelines_are_deterministic_over_many_launches(case, rng):
+    """k_decim8 and the FP64 tensor-core table kernel hand their ring / staging / tap-row buffers around with mbarriers only
+    (no CTA barrier; racecheck cannot follow a bulk-copy refill ordered by an mbarrier).  The same stream of chunks twice
+    through fresh filters: every chunk must come out BIT-identical -- a race shows up as a differing chunk (tools/
+    soak_new_kernels.py is the long form, 2 x 1500 chunks, profiles/r2_soak_new_kernels.txt)."""
+    import torch
+    N = 32
+    if case == "decim8":
+        ratio, h, extra, dt, tdt, want = Fraction(1, 8), mo.firdes(256, 0.5 / 8, 7.8562).astype(np.float32), (), np.complex64, torch.complex64, "decim8_c64"
+    else:
+        hLen, beta = mo.kaiserlength(0.05, samplerate=N)
+        hLen = -(-hLen // N) * N
+        h = (mo.firdes(hLen, 0.45, beta, samplerate=32) * N).astype(np.float64)
+        ratio, extra, dt, tdt, want = 0.918734, ((N,) if case == "f64_arbitrary_dmma" else (N, 4)), np.float64, torch.float64, "table_f64_dmma"
+    nch, n, steps = 512, 32768, 150
+    torch.manual_seed(11)
+    xs = [torch.randn((nch, n), device="cuda", dtype=tdt) for _ in range(3)]
+    sums = []
+    for _ in range(2):
+        f = mr.FIRFilter(h, ratio, *extra, nchannels=nch, sample_dtype=dt)
+        cs = []
+        for i in range(steps):
+            y = f.filt(xs[i % 3])
+            bits = torch.view_as_real(y).view(torch.int32) if tdt == torch.complex64 else y.view(torch.int64)
+            cs.append(bits.to(torch.int64).sum())
+        torch.cuda.synchronize()
+        assert f.last_kernel == want, f.last_kernel
+        sums.append(torch.stack(cs).cpu())
+    assert int((sums[0] != sums[1]).sum()) == 0
+
+
 @pytest.mark.parametrize("ntaps,nch", [(256, 300), (255, 129), (100, 512), (9, 160)])
 def test_decimator_m8_lane_per_channel_kernel(ntaps, nch, rng):
     """k_decim8 (mrb_decim.cuh): 1//8 on complex64 with the taps as launch constants -- ragged tap and channel counts, chunk
