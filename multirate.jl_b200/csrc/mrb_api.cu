@@ -962,6 +962,16 @@ static void launch_history(const mrb_filter *f, const void *x, int64_t ldx, int6
     }
 }
 
+// side stream of a table context: the chunk head runs there beside the main kernel (MRB_NO_SIDE_STREAM=1: same stream)
+static int32_t ensure_side(TableCtx &c) {
+    static const bool no_side = getenv("MRB_NO_SIDE_STREAM") != nullptr;
+    if (no_side || c.side) return MRB_OK;
+    CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    return MRB_OK;
+}
+
 static int32_t ensure_sched(mrb_filter *f, TableCtx &c) {
     if (c.ready) return MRB_OK;
     for (auto &s : c.slot) {
@@ -971,11 +981,9 @@ static int32_t ensure_sched(mrb_filter *f, TableCtx &c) {
     }
     if (f->kind == MRB_FARROW)
         CU(cudaMalloc(&c.d_taptab, (size_t)kSchedChunk * f->T * (is_double(f->ty) ? 8 : 4)));
-    static const bool no_side = getenv("MRB_NO_SIDE_STREAM") != nullptr;
-    if (!no_side && !f->mma.ok) {      // (the tensor-core kernel computes its head itself)
-        CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    if (!f->mma.ok) {                  // (the tensor-core kernel computes its head itself)
+        int32_t rc = ensure_side(c);
+        if (rc) return rc;
     }
     c.ready = true;
     return MRB_OK;
@@ -1027,6 +1035,15 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                     if (k_begin == -2) return fail(MRB_ERR_CUDA, "tensor-core launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 }
             }
+            // decimators: the chunk head (outputs whose long windows reach the history: 20 us of k_head_warp at C2 beside 174 us
+            // of main kernel) runs on the side stream, forked here and joined below
+            TableCtx &tci = f->tctx[ctx];
+            const bool may_fork = f->policy != 1 && f->kind == MRB_DECIMATOR && f->decim.ok && k_begin == -1;
+            if (may_fork) {
+                int32_t rc = ensure_side(tci);
+                if (rc) return rc;
+                if (tci.side) CU(cudaEventRecord(tci.ev_fork, st));
+            }
             if (k_begin == -1 && f->policy != 1) {
                 k_begin = tiled_try_launch(f->tiled, P, st, &f->last_kernel, &f->launches);
                 if (k_begin == -1) k_begin = unit_try_launch(f->unit, P, st, &f->last_kernel, &f->launches);
@@ -1034,10 +1051,15 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 if (k_begin == -2) return fail(MRB_ERR_CUDA, "fast-path launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
             if (k_begin != 0) {            // generic kernel: everything, or the head the tiled kernel left out
-                if (k_begin > 0) P.nout = k_begin;
-                const char *gname = dispatch_generic(f, P, st);
+                cudaStream_t hs = st;
+                if (k_begin > 0) {
+                    P.nout = k_begin;
+                    if (may_fork && tci.side && k_begin * nc >= 8192) { CU(cudaStreamWaitEvent(tci.side, tci.ev_fork, 0)); hs = tci.side; }
+                }
+                const char *gname = dispatch_generic(f, P, hs);
                 if (k_begin < 0) f->last_kernel = gname;
                 ++f->launches;
+                if (hs != st) { CU(cudaEventRecord(tci.ev_join, hs)); CU(cudaStreamWaitEvent(st, tci.ev_join, 0)); }
             }
         } else {
             TableCtx &tc = f->tctx[ctx];
