@@ -1,6 +1,7 @@
 # round 2 final evidence: full GPU suite, default bench line, reference arm, launch lists
 o=gpurun_out; mkdir -p $o
 timeout 900 python -m pytest tests -m gpu -q --timeout 200 2>&1 | tail -5 > $o/r2_pytest_gpu.txt; cat $o/r2_pytest_gpu.txt
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 1500 python bench.py --steps 20 --warmup 3 > $o/r2_bench_default.json 2> $o/r2_bench_default.err; echo "bench rc=$?"
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $o/r2_bench_reference_arm.json 2>> $o/r2_bench_default.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 16 -c 8 --csv --log-file $o/r2_ncu_launches_c2.csv python tools/mma_one.py c2 > /dev/null 2>&1
