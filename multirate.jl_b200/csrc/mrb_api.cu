@@ -416,7 +416,7 @@ extern "C" int32_t mrb_create(const mrb_desc *d, mrb_filter **out) {
         if (rc != 0) return fail(MRB_ERR_CUDA, "unit_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
         rc = decim_prepare(f->decim, kind, f->tx, f->ty, f->L, f->M, f->T, f->bank, prop);
         if (rc != 0) return fail(MRB_ERR_CUDA, "decim_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
-        rc = table_prepare(f->table, kind, f->tx, f->ty, f->T, f->rate, prop);
+        rc = table_prepare(f->table, kind, f->tx, f->ty, f->T, (kind == MRB_ARBITRARY || kind == MRB_FARROW) ? f->rate : (double)f->L / (double)f->M, prop);
         if (rc != 0) return fail(MRB_ERR_CUDA, "table_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
         rc = mma_prepare(f->mma, kind, f->tx, f->ty, f->th, f->T, prop);
         if (rc != 0) return fail(MRB_ERR_CUDA, "mma_prepare failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -1049,6 +1049,18 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 if (k_begin == -1) k_begin = unit_try_launch(f->unit, P, st, &f->last_kernel, &f->launches);
                 if (k_begin == -1) k_begin = decim_try_launch(f->decim, P, st, &f->last_kernel, &f->launches);
                 if (k_begin == -2) return fail(MRB_ERR_CUDA, "fast-path launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+            if (k_begin == -1 && f->policy != 1 && f->table.ok && nc >= 32) {
+                // Float64 samples: the table kernel's FP64 tensor-core variant with the schedule in closed form (64-channel
+                // CTAs: with a handful of channels k_stream wins)
+                GenParams Pt = P;
+                Pt.sn = nullptr; Pt.sphi = nullptr; Pt.salpha = nullptr;
+                // outputs whose window reaches the history: n_k < H  <=>  k < ceil(((H - d0m1) L - p0) / M)
+                const int64_t head = std::min<int64_t>(N, std::max<int64_t>(0, ceil_div((f->H - P.d0m1) * f->L - P.p0, f->M)));
+                k_begin = table_try_launch(f->table, tci.rows, Pt, f->kind, 1, f->th == MRB_F32, f->d_bank, nullptr, nullptr,
+                                           (double)f->L / (double)f->M, 0, N, head, (7 * f->M) / f->L + 1, st, &f->last_kernel,
+                                           &f->launches, 0);
+                if (k_begin == -2) return fail(MRB_ERR_CUDA, "table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
             if (k_begin != 0) {            // generic kernel: everything, or the head the tiled kernel left out
                 cudaStream_t hs = st;

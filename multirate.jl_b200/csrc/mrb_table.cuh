@@ -66,20 +66,24 @@ __global__ void __launch_bounds__(256)
 k_table_rows(const R *__restrict__ pfb, const R *__restrict__ dpfb, const double *__restrict__ pnfb, int P1, int T,
              int rowlen, int farrow, int tap_is_f32, const int64_t *__restrict__ sn, const int32_t *__restrict__ sphi,
              const double *__restrict__ sa, int64_t H, int64_t nout, R *__restrict__ rows, int32_t *__restrict__ astart,
-             int A) {
+             int A, int64_t iL = 0, int64_t iM = 0, int64_t ip0 = 0, int64_t id0m1 = 0) {
     // one warp per output row (8 rows per block): the row's schedule entries are read once, no index division
     const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= nout) return;
     const int lane = threadIdx.x & 31;
     // the kTabGroup outputs of a group read ONE register window that starts at the aligned window start of the
     // group's first output; every row of the group is shifted to its own place inside that window
-    const int64_t xs = sn[k] - H;                                    // x index of the window start (may be < 0: head)
-    const int64_t xg = sn[k / kTabGroup * kTabGroup] - H;
+    // sn == nullptr: an integer schedule in closed form (src/Filters.jl:558-569: n_k = d + floor((p + k M) / L), branch
+    // (p + k M) mod L; no blend) -- rational / interpolator / standard filters on Float64 samples
+    const bool closed = sn == nullptr;
+    const int64_t kg0 = k / kTabGroup * kTabGroup;
+    const int64_t xs = (closed ? id0m1 + (ip0 + k * iM) / iL : sn[k]) - H;       // x index of the window start (may be < 0: head)
+    const int64_t xg = (closed ? id0m1 + (ip0 + kg0 * iM) / iL : sn[kg0]) - H;
     const int64_t al = xg >= 0 ? xg / A * A : -((-xg + A - 1) / A) * A;
     const int d = (int)(xs - al);
     if (lane == 0) astart[k] = (int32_t)al;
-    const double ph = sa[k];                                         // farrow: phase; arbitrary: alpha
-    const int64_t obase = farrow ? 0 : (int64_t)sphi[k] * T;
+    const double ph = closed ? 0.0 : sa[k];                          // farrow: phase; arbitrary: alpha
+    const int64_t obase = farrow ? 0 : (closed ? (ip0 + k * iM) % iL : (int64_t)sphi[k]) * T;
     for (int j = lane; j < rowlen; j += 32) {
         const int i = j - d;
         R v = R(0);
@@ -93,7 +97,7 @@ k_table_rows(const R *__restrict__ pfb, const R *__restrict__ dpfb, const double
                 if (tap_is_f32) a = (double)(float)a;
                 v = (R)a;
             } else {
-                v = (R)((double)pfb[obase + i] + ph * (double)dpfb[obase + i]);
+                v = closed ? pfb[obase + i] : (R)((double)pfb[obase + i] + ph * (double)dpfb[obase + i]);
             }
         }
         rows[k * rowlen + j] = v;
@@ -547,7 +551,10 @@ static inline int table_smem(const TabPlan &p) {
 // kind/tx/ty are the mrb.h enums (4 arbitrary, 5 farrow ; 0 = float32, 1 = float64, 2 = complex64)
 static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_t T, double rate, const cudaDeviceProp &prop) {
     p.ok = false;
-    if (!(kind == 4 || kind == 5)) return 0;
+    // arbitrary / farrow; and -- Float64 samples only, on the FP64 tensor-core variant -- the integer kinds whose windows fit the
+    // ring (standard, interpolator, rational, gentle decimators: every Float64 call used to land on k_stream)
+    const bool int_kind = kind >= 0 && kind <= 3;
+    if (!(kind == 4 || kind == 5 || (int_kind && tx == 1 && ty == 1))) return 0;
     if (tx != ty || !(tx == 0 || tx == 1 || tx == 2)) return 0;         // float32, float64, complex64; no promotion
     p.K = tx == 0 ? TAB_F32 : tx == 1 ? TAB_F64 : TAB_C64;
     if (p.K == TAB_F32) { p.es = 4; p.ts = 4; p.A = 4; p.TB = TabCfg<TAB_F32>::TB; p.NB = TabCfg<TAB_F32>::NB; }
@@ -574,6 +581,7 @@ static inline int32_t table_prepare(TabPlan &p, int kind, int tx, int ty, int64_
         q.dm = dw && atoi(dw) == 4 ? 4 : 8; q.TB = 4; q.NB = kTabNB2; q.rowlen = (int)rl; q.nblk = (int)(rl / 4);
         if (!nd && rl <= 256 && table_smem(q) <= (int)prop.sharedMemPerBlockOptin) p = q;
     }
+    if (int_kind && p.dm == 0) return 0;
     if (p.dm == 0) {
     if (p.ch == 2) { p.TB = kTabTB2; p.NB = kTabNB2; }
     p.nblk = (int)ceil_div(T + p.A - 1 + gspan, p.TB);
@@ -667,7 +675,7 @@ static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams 
         if (p.K == TAB_F64)
             k_table_rows<double><<<g, 256, 0, st>>>((const double *)d_pfb, (const double *)d_dpfb, d_pnfb, P1, p.T, p.rowlen,
                                                     kind == 5, tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt,
-                                                    (double *)rw.d_rows, rw.d_astart, A);
+                                                    (double *)rw.d_rows, rw.d_astart, A, G.L, G.M, G.p0, G.d0m1);
         else
             k_table_rows<float><<<g, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, p.rowlen,
                                                    kind == 5, tap_is_f32, G.sn, G.sphi, G.salpha, G.H, cnt,
@@ -719,7 +727,7 @@ static inline int64_t table_try_launch(TabPlan &p, TabRows &rw, const GenParams 
         else k_table_fir<TAB_C64, 48, 1><<<grid, 128, smem, st>>>(tmx, tmy, (const float *)rw.d_rows, rw.d_astart, P);
     }
     if (cudaPeekAtLastError() != cudaSuccess) return -2;
-    *name = p.K == TAB_F32 ? "table_f32" : p.K == TAB_F64 ? (p.dm ? "table_f64_dmma" : p.ch == 2 ? "table_f64_2ch" : "table_f64") : "table_c64";
+    *name = p.K == TAB_F32 ? "table_f32" : p.K == TAB_F64 ? (p.dm ? (kind <= 3 ? "int_f64_dmma" : "table_f64_dmma") : p.ch == 2 ? "table_f64_2ch" : "table_f64") : "table_c64";
     ++*launches;
     return k_begin;
 }

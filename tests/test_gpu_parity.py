@@ -582,10 +582,47 @@ def test_stream_kernel_few_channels(ratio, ntaps, th, tx, nch, rng):
         if y.shape[1] >= 8192:
             used.add(f.last_kernel)
         assert g.last_kernel in ("generic", "none")
-    # the long chunks never fall back to k_generic; Float64 work has no other fast path than k_stream
+    # the long chunks never fall back to k_generic; with a few channels Float64 work runs on k_stream (from 32 channels on:
+    # the FP64 tensor-core kernel, test_float64_integer_kinds_on_fp64_tensor_cores)
     assert used and "generic" not in used, used
     if th == np.float64:
         assert used == {"stream"}, used
+
+
+@pytest.mark.parametrize("ratio,ntaps", [(Fraction(147, 160), 3528), (Fraction(4, 1), 128), (Fraction(1, 1), 63), (Fraction(3, 2), 90),
+                                         (Fraction(2, 3), 50), (Fraction(160, 147), 3200)])
+@pytest.mark.parametrize("th", [np.float64, np.float32])
+def test_float64_integer_kinds_on_fp64_tensor_cores(ratio, ntaps, th, rng):
+    """Standard / interpolator / rational filters on Float64 samples: the table kernel's mma.sync.m8n8k4 variant with the
+    schedule in closed form (mrb_table.cuh k_table_rows, sn == nullptr).  Ragged channel count, chunk edges that leave every
+    phase / deficit behind, state carried; against the oracle and k_generic."""
+    import torch
+    h = rng.standard_normal(ntaps).astype(th)
+    nch = 70
+    big = (int(9000 / ratio) + 2) // 2 * 2                          # even: 16-byte aligned chunk starts and row pitch
+    # (the chunk that starts at the odd edge takes the unaligned fallback, k_stream)
+    edges = [0, big, big + 2, big + 502, 2 * big + 502, 2 * big + 503, 3 * big + 700]
+    n = edges[-1]
+    x = rand_samples(rng, (nch, n), np.float64)
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=np.float64)
+    g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=np.float64)
+    g.set_kernel_policy(1)
+    o = mo.FIRFilter(h, ratio)
+    rows = [0, 1, 35, nch - 1]
+    used = set()
+    for a, b in zip(edges[:-1], edges[1:]):
+        yd = f.filt(xd[:, a:b])
+        yg = g.filt(xd[:, a:b])
+        w = o.filt(x[rows, a:b])
+        torch.cuda.synchronize()
+        y = yd.cpu().numpy()
+        assert y.shape == (nch, w.shape[1])
+        assert nerr(y[rows], w) <= tol_for(y.dtype), (a, b, nerr(y[rows], w))
+        assert nerr(yg.cpu().numpy(), y) <= 1e-13
+        assert states_equal(f, o)
+        used.add(f.last_kernel)
+    assert "int_f64_dmma" in used, used
 
 
 @pytest.mark.parametrize("tx", [np.float32, np.float64, np.complex64])
