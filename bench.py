@@ -72,15 +72,17 @@ WORKLOADS = {
               5.6533, 32.0, np.float32, 8192, 32, None),
     "xr32": ("extra: FIRRational 147//160, 3528 taps, 8192 ch float32 (the README dtype, multichannel)", Fraction(147, 160), 3528,
              0.5 / 147, 7.8562, 1.0, np.float32, 8192, None, None),
+    "xr64": ("extra: FIRRational 147//160, 3528 taps, 4096 ch float64 (integer kinds on the FP64 tensor-core kernel)", Fraction(147, 160),
+             3528, 0.5 / 147, 7.8562, 1.0, np.float64, 4096, None, None),
 }
-EXTRA_CONFIGS = ["c1", "c2", "c3a", "c3b", "c4a", "c4f", "c4a64", "c4f64", "xr32", "x4a8k"]   # the BASELINE configs + two extras
+EXTRA_CONFIGS = ["c1", "c2", "c3a", "c3b", "c4a", "c4f", "c4a64", "c4f64", "xr32", "x4a8k", "xr64"]   # the BASELINE configs + three extras
 # taps per output and the bound SURVEY 8d assigns (roofline denominators: measured HBM; nominal FP32 / FP64 FMA rate)
 TAPS_PER_OUT = {"c5": 24, "c1": 24, "c2": 256, "c3a": 32, "c3b": 128, "c4a": 73, "c4f": 73, "c4a64": 73, "c4f64": 73,
-                "x160": 24, "x2f": 256, "x3ac": 32, "x3bc": 128, "x4ac": 73, "x4fc": 73, "x4a8k": 73, "xr32": 24}
+                "x160": 24, "x2f": 256, "x3ac": 32, "x3bc": 128, "x4ac": 73, "x4fc": 73, "x4a8k": 73, "xr32": 24, "xr64": 24}
 # (c3b / c4a / c4f were FP32-FMA bound on CUDA cores per SURVEY 8d; on the tensor-core kernel their roof is HBM: both are given)
 BOUND = {"c5": "hbm", "c1": "latency", "c2": "fp32", "c3a": "hbm", "c3b": "fp32", "c4a": "fp32", "c4f": "fp32",
          "c4a64": "fp64", "c4f64": "fp64", "x160": "hbm", "x2f": "fp32", "x3ac": "hbm", "x3bc": "fp32", "x4ac": "fp32",
-         "x4fc": "fp32", "x4a8k": "fp32", "xr32": "hbm"}
+         "x4fc": "fp32", "x4a8k": "fp32", "xr32": "hbm", "xr64": "hbm"}
 FP32_PEAK_TF = 148 * 128 * 2 * 1.965e9 / 1e12          # nominal CUDA-core FP32, TFLOP/s
 README_ONESHOT_S = 0.056938961                          # README.md:190-193, the only number upstream publishes
 
