@@ -191,6 +191,8 @@ struct alignas(16) MmaParams {
     int nissue;                // 2: a look-ahead warp does the issuer's waits (default); 1: the issuer waits itself (MRB_MMA_ISSUERS=1)
     int period;                // tile of group g = tile (g mod period): g_end - 0 for aperiodic tables
     int resident;              // period <= NWB: every tile is loaded once and stays in its slot
+    int fwd;                   // 1: the epilogue releases tile slots and ring boxes once it sees the group's accumulators complete
+                               // (one tcgen05.commit per group instead of three or four on the issuing thread); 0: MRB_MMA_FWD=0
     int nch;                   // channels (rows past it read zero history)
     const float *hist;         // [nch][H] history of the chunk: samples at x indices -H .. -1
     long long H;
@@ -435,9 +437,13 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
                 case 23: mma_issue_group<G, 23>(d, ah, al, col0, bh0, lo_off, idesc); break;
                 default: mma_issue_group<G, 24>(d, ah, al, col0, bh0, lo_off, idesc); break;
                 }
-                tc_commit(B_WEMPTY(ws));                               // the tile slot may be refilled
+                // The issuing thread is the kernel's bottleneck (per group: 20 cycles per MMA + ~320 of fixed cost, most of it
+                // commits): ONE commit hands the accumulators over, the epilogue -- which then knows that every MMA of the group
+                // is done -- releases the tile slot and the dead ring boxes with plain arrivals (P.fwd).
+                if (!P.fwd && !P.resident) tc_commit(B_WEMPTY(ws));    // the tile slot may be refilled (resident: never refilled)
                 tc_commit(B_DFULL(w & 1));                             // the accumulators are complete
-                for (int b = dead; b < next_first; ++b) tc_commit(B_AEMPTY(b % NAB));   // ring boxes nobody reads any more
+                if (!P.fwd)
+                    for (int b = dead; b < next_first; ++b) tc_commit(B_AEMPTY(b % NAB));   // ring boxes nobody reads any more
             }
             __syncwarp();
             if (prof) c3 += clock64() - ti0;
@@ -502,9 +508,17 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
         const int row = warp * 32 + lane;
         const uint32_t lanebase = tb + ((uint32_t)(warp * 32) << 16);
         const uint32_t rowpart = ((uint32_t)row * 128u) ^ (((uint32_t)row & 7u) << 4);
+        int dead_e = 0, ws_e = 0;                                      // (warp 1 lane 0) boxes and tile slot released so far
         for (int w = 0; w < ng; ++w) {
             mbar_wait_prof(B_DFULL(w & 1), (uint32_t)((w / 2) & 1), prof, c0);
             tc_fence_after();
+            if (P.fwd && tid == 32) {
+                // every MMA of group w has completed: its tile slot and the ring boxes before the next group's window are free
+                if (!P.resident) { mbar_arrive(B_WEMPTY(ws_e)); if (++ws_e == P.NWB) ws_e = 0; }
+                const int next_first = w + 1 < ng ? (gs[w + 1] - xbase) / kMmaBox : jlast + 1;
+                for (int b = dead_e; b < next_first; ++b) mbar_arrive(B_AEMPTY(b % NAB));
+                if (next_first > dead_e) dead_e = next_first;
+            }
             uint32_t v[G];
             tmem_ld16(lanebase + (uint32_t)(C::TM_D + (w & 1) * G), v);
             tmem_ld16(lanebase + (uint32_t)(C::TM_D + (w & 1) * G + 16), v + 16);
@@ -653,6 +667,8 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     P.prof = want_prof ? d_prof : nullptr;
     P.g_begin = g_begin; P.g_end = groups; P.y0 = y0; P.KB = KB; P.KS = KS; P.NWB = nwb; P.tile_bytes = tile_bytes;
     P.period = (int)ntiles; P.resident = resident ? 1 : 0;
+    static const int fwd = getenv("MRB_MMA_FWD") && atoi(getenv("MRB_MMA_FWD")) == 0 ? 0 : 1;
+    P.fwd = fwd;
     static const int n_issuers = getenv("MRB_MMA_ISSUERS") && atoi(getenv("MRB_MMA_ISSUERS")) == 1 ? 1 : 2;
     P.nissue = n_issuers;
     P.nch = (int)G.nch; P.hist = static_cast<const float *>(G.hist); P.H = G.H;
