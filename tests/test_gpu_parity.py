@@ -623,6 +623,13 @@ def test_float64_integer_kinds_on_fp64_tensor_cores(ratio, ntaps, th, rng):
         assert states_equal(f, o)
         used.add(f.last_kernel)
     assert "int_f64_dmma" in used, used
+    # host buffers of odd length: mrb_filt_host stages them with 16-byte row pitches, so the fast path still applies
+    fh = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=np.float64)
+    oh = mo.FIRFilter(h, ratio)
+    m = big + 501
+    yh = fh.filt(np.ascontiguousarray(x[:, :m]))
+    assert nerr(np.asarray(yh)[rows], oh.filt(x[rows, :m])) <= tol_for(np.float64)
+    assert fh.last_kernel == "int_f64_dmma", fh.last_kernel
 
 
 @pytest.mark.parametrize("tx", [np.float32, np.float64, np.complex64])
