@@ -1026,12 +1026,20 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 static const bool mma_int = !(getenv("MRB_MMA_INT") && atoi(getenv("MRB_MMA_INT")) == 0);
                 // short single-rate filters are HBM bound on the CUDA cores already (standard, 32 taps: k_unit_f32 730 Gout/s,
                 // tensor-core kernel 592); from ~48 taps on the tensor cores win (128 taps: 438 against 227)
-                const bool unit_better = f->unit.ok && f->L == 1 && f->M == 1 && f->T <= 48;
+                const bool cx = f->mma.cplx != 0;                  // complex64: the kernel runs on the float view of x, y, history
+                // complex64 (measured): rational 147//160 326.7 against 310.7 on k_tiled_c64, 160//147 355 against 286; the unit
+                // kernel keeps standard / interpolator L in {1,2,4} (4//1: 434 against 407), k_decim / k_decim8 the decimators
+                const bool unit_better = cx ? (f->unit.ok || (f->kind == MRB_DECIMATOR && f->decim.ok))
+                                            : (f->unit.ok && f->L == 1 && f->M == 1 && f->T <= 48);
                 if (mma_int && !unit_better) {
                     MmaSched S{};
-                    S.mode = 2; S.L = f->L; S.M = f->M; S.p0 = P.p0; S.d0m1 = P.d0m1; S.k_base = 0;
-                    k_begin = mma_try_launch(f->mma, f->tctx[ctx].mrows, P, S, 0, f->d_bank, nullptr, nullptr, 0, N,
-                                             (31 * f->M) / f->L + 1, st, &f->last_kernel, &f->launches);
+                    S.mode = 2; S.L = f->L; S.M = f->M; S.p0 = P.p0; S.d0m1 = P.d0m1; S.k_base = 0; S.cplx = cx ? 1 : 0;
+                    GenParams Pv = P;
+                    if (cx) { Pv.ldx *= 2; Pv.n_in *= 2; Pv.H *= 2; Pv.ldy *= 2; }
+                    // widest spread of window starts in a group: 32 outputs, or 16 complex outputs seen as 32 floats
+                    const int64_t span = cx ? 2 * ((15 * f->M) / f->L + 1) + 1 : (31 * f->M) / f->L + 1;
+                    k_begin = mma_try_launch(f->mma, f->tctx[ctx].mrows, Pv, S, 0, f->d_bank, nullptr, nullptr, 0, cx ? 2 * N : N,
+                                             span, st, &f->last_kernel, &f->launches);
                     if (k_begin == -2) return fail(MRB_ERR_CUDA, "tensor-core launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 }
             }
@@ -1107,13 +1115,18 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                     while (head < cnt && vn[k0 + head] < f->H) ++head;
                     int64_t kb = -1;
                     if (f->mma.ok && f->policy == 0) {         // tensor cores first (float32 samples and taps)
-                        int64_t gs32 = 0;                      // widest spread of window starts inside a group of 32 outputs
-                        for (int64_t g0 = 0; g0 < cnt; g0 += kMmaG)
-                            gs32 = std::max(gs32, vn[k0 + std::min<int64_t>(g0 + kMmaG, cnt) - 1] - vn[k0 + g0]);
+                        const bool cx = f->mma.cplx != 0;      // complex64: float view, a group is 16 complex outputs
+                        const int64_t og = cx ? kMmaG / 2 : kMmaG;
+                        int64_t gs32 = 0;                      // widest spread of window starts inside a group
+                        for (int64_t g0 = 0; g0 < cnt; g0 += og)
+                            gs32 = std::max(gs32, vn[k0 + std::min<int64_t>(g0 + og, cnt) - 1] - vn[k0 + g0]);
                         MmaSched S{};
-                        S.mode = f->kind == MRB_FARROW ? 1 : 0; S.sn = s.d_n; S.sphi = s.d_phi; S.sa = s.d_a;
-                        kb = mma_try_launch(f->mma, tc.mrows, P, S, f->polyorder + 1, f->d_bank, f->d_dbank, f->d_pnfb, k0, cnt, gs32, st,
-                                            &f->last_kernel, &f->launches, tag);
+                        S.mode = f->kind == MRB_FARROW ? 1 : 0; S.sn = s.d_n; S.sphi = s.d_phi; S.sa = s.d_a; S.cplx = cx ? 1 : 0;
+                        GenParams Pv = P;
+                        if (cx) { Pv.ldx *= 2; Pv.n_in *= 2; Pv.H *= 2; Pv.ldy *= 2; gs32 = 2 * gs32 + 1; }
+                        kb = mma_try_launch(f->mma, tc.mrows, Pv, S, f->polyorder + 1, f->d_bank, f->d_dbank, f->d_pnfb, cx ? 2 * k0 : k0,
+                                            cx ? 2 * cnt : cnt, gs32, st, &f->last_kernel, &f->launches, tag);
+                        if (cx && kb > 0) kb /= 2;
                         if (kb == -2) return fail(MRB_ERR_CUDA, "tensor-core launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                     }
                     int64_t gspan = 0;                         // widest spread of window starts inside a group of 8 outputs

@@ -106,9 +106,15 @@ struct MmaSched {               // where the pre-pass takes an output's (window 
     const double *sa;           // mode 0: alpha; mode 1: Float64 phase
     long long L, M, p0, d0m1;   // mode 2: n_k = d0m1 + (p0 + k M) / L, branch (p0 + k M) % L   (k = slice-relative + k_base)
     long long k_base;
+    // complex64 samples x real taps: the kernel runs on the FLOAT view of x and y (interleaved re, im).  Float output j = 2k + b
+    // is output k's part b: its window ends at float 2 n_k + b and holds tap i of the branch at window position 2i (the odd
+    // positions -- the other part's samples -- are zeros): a real FIR of 2T - 1 taps with the schedule below.  Same bytes per
+    // float as the real kernel, twice the MMAs per output (the pipe has the room: 26 % active on the float32 resampler).
+    int cplx;
 };
 
-__device__ __forceinline__ void mma_sched_at(const MmaSched &S, int64_t k, int64_t &n, int64_t &phi) {
+__device__ __forceinline__ void mma_sched_at(const MmaSched &S, int64_t kf, int64_t &n, int64_t &phi) {
+    const int64_t k = S.cplx ? kf >> 1 : kf;                           // output index (kf: float index of the interleaved view)
     if (S.mode == 2) {
         const long long t = S.p0 + (S.k_base + k) * S.M;
         const long long q = t / S.L;
@@ -118,6 +124,7 @@ __device__ __forceinline__ void mma_sched_at(const MmaSched &S, int64_t k, int64
         n = S.sn[k];
         phi = S.mode == 0 ? S.sphi[k] : 0;
     }
+    if (S.cplx) n = 2 * n + (kf & 1);
 }
 
 // Rows [0, nrows) of the tile table (nrows = tiles * G; for periodic integer schedules only one period of tiles is
@@ -149,14 +156,16 @@ k_mma_tiles(const float *__restrict__ pfb, const float *__restrict__ dpfb, const
     int64_t nk = 0, phik = 0;
     if (live) mma_sched_at(S, k, nk, phik);
     const int d = live ? (int)(nk - H - al) : 0;
-    const double ph = live && S.mode != 2 ? S.sa[k] : 0.0;           // farrow: phase; arbitrary: alpha
+    const double ph = live && S.mode != 2 ? S.sa[S.cplx ? k >> 1 : k] : 0.0;   // farrow: phase; arbitrary: alpha
+    const int Tw = S.cplx ? 2 * T - 1 : T;                           // window length in elements of the (float) view
     const int64_t obase = phik * T;
     const int64_t tile_floats = (int64_t)2 * KB * G * 32;
     float *th = tiles + g * tile_floats, *tl = th + (int64_t)KB * G * 32;
     for (int j = lane; j < KB * 32; j += 32) {
-        const int i = j - d;
+        const int iw = j - d;                                        // window position
+        const int i = S.cplx ? iw >> 1 : iw;                         // tap (complex view: taps sit at the even positions)
         float v = 0.f;
-        if (live && i >= 0 && i < T) {
+        if (live && iw >= 0 && iw < Tw && !(S.cplx && (iw & 1))) {
             if (S.mode == 1) {
                 // currentTaps[i] = polyval(pnfb[i], phase): Horner highest order first in Float64, separately rounded
                 // multiply and add, rounded to the tap type (src/Filters.jl:789-791)
@@ -575,6 +584,7 @@ static inline void mmarows_release(MmaRows &r) {
 
 struct MmaPlan {
     bool ok = false;
+    int cplx = 0;                      // complex64 samples: every launch works on the float view (see MmaSched::cplx)
     int T = 0;
     PFN_encodeTiled encode = nullptr;
     int num_sms = 148;
@@ -587,8 +597,12 @@ static inline void mma_release(MmaPlan &p) { p.ok = false; }
 static inline int32_t mma_prepare(MmaPlan &p, int kind, int tx, int ty, int th, int64_t T, const cudaDeviceProp &prop) {
     p.ok = false;
     static const bool off = getenv("MRB_NO_MMA") != nullptr;
-    if (off || kind < 0 || kind > 5 || tx != 0 || ty != 0 || th != 0) return 0;
-    if (T + 7 > kMmaMaxKB * 32) return 0;
+    static const bool no_c64 = getenv("MRB_MMA_C64") && atoi(getenv("MRB_MMA_C64")) == 0;
+    // float32 samples, or complex64 samples through their float view (tx / ty: 0 = float32, 2 = complex64); float32 taps
+    const bool real = tx == 0 && ty == 0, cplx = tx == 2 && ty == 2 && !no_c64;
+    if (off || kind < 0 || kind > 5 || !(real || cplx) || th != 0) return 0;
+    p.cplx = cplx ? 1 : 0;
+    if ((cplx ? 2 * T - 1 : T) + 7 > kMmaMaxKB * 32) return 0;
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -631,7 +645,8 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     // a CTA is 128 channels wide (UMMA M): with a handful of channels the other kernels win (README benchmark, ONE channel:
     // k_stream 0.024 ms, this kernel 0.19 ms)
     if (G.nch < 48) MRB_MMA_SKIP("too few channels for a 128-row tile");
-    const int64_t kneed = p.T + 7 + max_group_span;                   // samples a group's window spans at worst
+    const int64_t Tw = S.cplx ? 2 * (int64_t)p.T - 1 : p.T;           // window length in elements of the view
+    const int64_t kneed = Tw + 7 + max_group_span;                    // samples a group's window spans at worst
     const int KB = (int)ceil_div(kneed, 32);
     if (KB > kMmaMaxKB) MRB_MMA_SKIP("window group wider than the tensor-memory ring");
     const int KS = (int)ceil_div(kneed, 8);
@@ -649,8 +664,9 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     // interpolators: ONE tile, kept resident in shared memory; 147//160: 147 tiles, L2 resident).
     int64_t period = groups;
     if (S.mode == 2) {
-        for (int64_t q = 1; q <= std::min<int64_t>(groups, 8 * S.L); ++q)
-            if ((q * GG * S.M) % S.L == 0 && ((q * GG * S.M) / S.L) % 8 == 0) { period = q; break; }
+        const int64_t og = S.cplx ? GG / 2 : GG, adv = S.cplx ? 2 : 1;       // outputs per group; view elements per input sample
+        for (int64_t q = 1; q <= std::min<int64_t>(groups, 16 * S.L); ++q)
+            if ((q * og * S.M) % S.L == 0 && (((q * og * S.M) / S.L) * adv) % 8 == 0) { period = q; break; }
     }
     const int64_t ntiles = std::min(period, groups);
     const bool resident = S.mode == 2 && period <= nwb;
@@ -744,7 +760,7 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
                     (long long)(cgroups * tiles), s[9], s[10], s[0], s[1], s[2], s[3], s[4], s[15], s[11], s[14], s[5], s[6], s[13], s[7], s[8], s[12]);
         }
     }
-    *name = resident ? "mma_f32_g32_resident" : "mma_f32_g32";
+    *name = S.cplx ? (resident ? "mma_c64_g32_resident" : "mma_c64_g32") : (resident ? "mma_f32_g32_resident" : "mma_f32_g32");
     ++*launches;
     return k_begin;
 }

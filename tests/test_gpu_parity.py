@@ -679,7 +679,7 @@ def test_host_path_uses_fast_kernels_for_any_length(case, rng):
     N = 32
     hl, beta = mo.kaiserlength(0.05, samplerate=N)
     ha = (mo.firdes(-(-hl // N) * N, 0.45, beta, samplerate=32) * N).astype(np.float32)
-    cfg = {"rational": (Fraction(147, 160), mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32), np.complex64, "tiled"),
+    cfg = {"rational": (Fraction(147, 160), mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32), np.complex64, "mma_c64"),
            "decimator": (Fraction(1, 8), mo.firdes(256, 0.5 / 8, 7.8562).astype(np.float32), np.complex64, "decim"),
            "interpolator": (Fraction(4, 1), mo.firdes(128, 0.5 / 4, 7.8562).astype(np.float32), np.float32, "mma"),
            "standard": (Fraction(1, 1), mo.firdes(128, 0.25, 7.8562).astype(np.float32), np.float32, "mma"),
@@ -730,14 +730,20 @@ def test_fast_paths_random_stress_against_generic_kernel(rng):
     for _ in range(3):                                             # decimator: float32, M in {4, 8}
         M = int(r.choice([4, 8]))
         cases.append((Fraction(1, M), int(r.integers(1, 32 * M + 1)), np.float32, "decim_f32"))
+    for _ in range(4):                                             # tensor cores: complex64 rational through the float view
+        M = int(r.integers(2, 60))
+        L = int(r.integers(M // 2 + 1, 2 * M))
+        while math.gcd(L, M) != 1 or L == M:
+            L = int(r.integers(M // 2 + 1, 2 * M))
+        cases.append((Fraction(L, M), int(r.integers(1, 40 * L + 1)), np.complex64, "mma_c64"))
     for ratio, ntaps, tx, want in cases:
         h = r.standard_normal(ntaps).astype(np.float32)
-        nch = int(r.integers(1, 200))
+        nch = int(r.integers(48, 200)) if want == "mma_c64" else int(r.integers(1, 200))
         n = 4 * int(r.integers(1500, 3000))
         x = torch.from_numpy(rand_samples(r, (nch, n), tx)).cuda()
         f = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
-        if want in ("unit", "decim_f32"):
-            f.set_kernel_policy(2)                                 # float32: keep to the CUDA-core fast paths here
+        if want in ("unit", "decim_f32", "tiled"):
+            f.set_kernel_policy(2)                                 # keep to the CUDA-core fast paths here (tensor cores: below)
         g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
         g.set_kernel_policy(1)
         cut = sorted(4 * int(v) for v in r.integers(1, n // 4, size=2))
