@@ -1,10 +1,8 @@
 o=gpurun_out; mkdir -p $o
 nvidia-smi -L | wc -l
-timeout 300 tools/h2d_ceiling 1024 4 0 > $o/r2_h2d_ceiling_n8.txt 2>&1; cat $o/r2_h2d_ceiling_n8.txt
-for n in 8 4; do
+for n in 8 4 2; do
 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 3 --only-main > $o/r2_bench_n$n.json 2> $o/r2_bench_n$n.err; echo "n$n rc=$?"
-tail -2 $o/r2_bench_n$n.err | cut -c1-300
 python -c "
 import json
-d=json.loads(open('$o/r2_bench_n$n.json').read().strip().splitlines()[-1]); print($n, round(d['value'],1), d['unit'], 'e2e', d['e2e']['value'], d['roofline']['frac'])"
+d=json.loads(open('$o/r2_bench_n$n.json').read().strip().splitlines()[-1]); print($n, round(d['value'],1), d['unit'], 'e2e', d['e2e']['value'], d['roofline']['frac'], d['roofline']['kernel'], d['clocks']['sm_mhz'])"
 done
