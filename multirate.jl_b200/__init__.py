@@ -12,11 +12,11 @@ from .sharding import LongStream, channel_shard, filt_long_stream, segment_bound
 from .firdesign import (BANDPASS, BANDSTOP, HIGHPASS, LOWPASS, FIRResponse, blackman, firdes, firprototype, hamming, hanning,
                         kaiser, kaiserlength)
 from .filters import (FIRArbitrary, FIRDecimator, FIRFarrow, FIRFilter, FIRInterpolator, FIRKernel, FIRRational,
-                      FIRStandard, filt, filt_, inputlength, nextphase, outputlength, pfb2pnfb, polyfit, reset,
+                      FIRStandard, clear_oneshot_cache, filt, filt_, inputlength, nextphase, outputlength, pfb2pnfb, polyfit, reset,
                       setphase, taps2pfb, tapsforphase, tapsforphase_)
 
 __all__ = ["FIRFilter", "FIRKernel", "FIRStandard", "FIRInterpolator", "FIRDecimator", "FIRRational", "FIRArbitrary",
            "FIRFarrow", "filt", "filt_", "reset", "setphase", "outputlength", "inputlength", "taps2pfb", "tapsforphase",
-           "tapsforphase_", "nextphase", "polyfit", "pfb2pnfb", "MrbError", "build", "channel_shard", "segment_bounds", "segment_plan", "filt_long_stream", "LongStream",
+           "tapsforphase_", "nextphase", "polyfit", "pfb2pnfb", "MrbError", "build", "channel_shard", "segment_bounds", "segment_plan", "filt_long_stream", "LongStream", "clear_oneshot_cache",
            "firdes", "firprototype", "kaiserlength", "FIRResponse", "LOWPASS", "BANDPASS", "HIGHPASS", "BANDSTOP", "kaiser",
            "hanning", "hamming", "blackman"]

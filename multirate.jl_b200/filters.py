@@ -576,7 +576,48 @@ def filt(a, x, *args, **kw):
     filt(h, x, rate, Nphi, polyorder)  (src/Filters.jl:858-873)."""
     if isinstance(a, FIRFilter):
         return a.filt(x)
-    return FIRFilter(a, *args, **kw).filt(x)
+    return _oneshot_filter(a, x, args, kw).filt(x)
+
+
+# One-shot calls build a filter, use it once and drop it: with a GPU behind it that is device allocations, a stream and the
+# plan tables -- 2-7 ms around a 0.03 ms kernel at the README's benchmark shape.  The handles of recent one-shot calls are
+# kept (per thread: a handle is not thread safe) and RESET -- mrb_reset is a full re-initialisation -- when the same taps,
+# ratio and input layout come again, so a repeated one-shot costs its copies and one launch.
+_ONESHOT_KEEP = 8
+_oneshot_tls = None
+
+
+def clear_oneshot_cache():
+    """Drop the handles kept for repeated one-shot filt(h, x, ...) calls (this thread's)."""
+    if _oneshot_tls is not None and getattr(_oneshot_tls, "cache", None):
+        _oneshot_tls.cache.clear()
+
+
+def _oneshot_filter(h, x, args, kw):
+    global _oneshot_tls
+    import threading
+    if _oneshot_tls is None:
+        _oneshot_tls = threading.local()
+    cache = getattr(_oneshot_tls, "cache", None)
+    if cache is None:
+        cache = _oneshot_tls.cache = {}
+    ha = np.ascontiguousarray(h)
+    try:
+        dev = ("host",) if isinstance(x, np.ndarray) or not hasattr(x, "device") else ("cuda", x.device.index)
+        shape = tuple(x.shape[:-1]) if getattr(x, "ndim", 1) > 1 else ()
+        key = (ha.tobytes(), str(ha.dtype), tuple(args), tuple(sorted(kw.items())), str(getattr(x, "dtype", None)), shape, dev)
+        hash(key)
+    except Exception:
+        return FIRFilter(h, *args, **kw)
+    f = cache.pop(key, None)
+    if f is None:
+        f = FIRFilter(h, *args, **kw)
+    else:
+        f.reset()
+    cache[key] = f                                                   # (re)inserted last: the dict is the LRU order
+    while len(cache) > _ONESHOT_KEEP:
+        cache.pop(next(iter(cache)))
+    return f
 
 
 def filt_(buffer, self, x):

@@ -457,6 +457,30 @@ def test_decimator_c64_kernel_shapes(M, ntaps, nch, tx, rng):
         assert any(k.startswith("decim_c64" if tx == np.complex64 else "decim_f32") for k in used), used
 
 
+def test_repeated_one_shot_calls_reuse_a_reset_handle(rng):
+    """filt(h, x, ratio) keeps the handle of a one-shot call and resets it when the same taps / ratio / layout come again:
+    the repeated call must equal a fresh filter's output bit for bit (mrb_reset is a full re-initialisation), for host and
+    device inputs, and a different input length or ratio must not be served by a stale state."""
+    import torch
+    h = mo.firdes(24 * 147, 0.5 / 147, 7.8562).astype(np.float32)
+    x = rand_samples(rng, (5000,), np.float32)
+    mr.clear_oneshot_cache()
+    y1 = mr.filt(h, x, Fraction(147, 160))
+    y2 = mr.filt(h, x, Fraction(147, 160))                          # served by the kept handle
+    y3 = mr.FIRFilter(h, Fraction(147, 160)).filt(x)
+    assert np.array_equal(y1, y2) and np.array_equal(y1, y3)
+    assert nerr(y1, mo.filt(h, x, Fraction(147, 160))) <= 1e-5
+    y4 = mr.filt(h, x[:3001], Fraction(147, 160))                   # same key, other length: state must start over
+    assert np.array_equal(y4, mr.FIRFilter(h, Fraction(147, 160)).filt(x[:3001]))
+    xd = torch.from_numpy(x).cuda()
+    y5, y6 = mr.filt(h, xd, Fraction(3, 2)), mr.filt(h, xd, Fraction(3, 2))
+    assert torch.equal(y5, y6) and nerr(y5.cpu().numpy(), mo.filt(h, x, Fraction(3, 2))) <= 1e-5
+    ya = mr.filt(h[:2336] * 32, x, 0.918734, 32, 4)
+    yb = mr.filt(h[:2336] * 32, x, 0.918734, 32, 4)
+    assert np.array_equal(ya, yb)
+    mr.clear_oneshot_cache()
+
+
 @pytest.mark.parametrize("case", ["decim8", "f64_arbitrary_dmma", "f64_farrow_dmma"])
 def test_mbarrier_pipelines_are_deterministic_over_many_launches(case, rng):
     """k_decim8 and the FP64 tensor-core table kernel hand their ring / staging / tap-row buffers around with mbarriers only
