@@ -457,6 +457,39 @@ def test_decimator_c64_kernel_shapes(M, ntaps, nch, tx, rng):
         assert any(k.startswith("decim_c64" if tx == np.complex64 else "decim_f32") for k in used), used
 
 
+@pytest.mark.parametrize("polyorder", [None, 4])
+def test_schedule_cache_is_keyed_by_state_and_length(polyorder, rng):
+    """Table kinds: the replayed schedule of a count query is reused by the filt call that follows only when (state, n_in)
+    are the same -- repeated lengths, another length, a state edit and a reset in between; counts, phase state and values
+    must be those of the oracle every time."""
+    import torch
+    N = 32
+    hLen, beta = mo.kaiserlength(0.05, samplerate=N)
+    hLen = -(-hLen // N) * N
+    h = (mo.firdes(hLen, 0.45, beta, samplerate=32) * N).astype(np.float32)
+    nch = 64
+    lens = [20000, 20000, 20000, 15000, 20000, 20001, 20001, 9000, 20000, 20000]
+    x = rand_samples(rng, (nch, sum(lens)), np.float32)
+    xd = torch.from_numpy(x).cuda()
+    f = mr.FIRFilter(h, 0.918734, N, polyorder)
+    o = mo.FIRFilter(h, 0.918734, N, polyorder)
+    a = 0
+    for i, n in enumerate(lens):
+        if i == 5:                                                 # a state edit between two calls (examples/FIRFarrow.jl:29)
+            f.kernel.inputDeficit += 3
+            o.kernel.inputDeficit += 3
+        if i == 8:
+            f.reset(); o.reset()
+        assert f.outputlength(n) >= 0                              # (the count query replays or adopts first, filt reuses it)
+        y = f.filt(xd[:, a:a + n])
+        w = o.filt(x[:2, a:a + n])
+        torch.cuda.synchronize()
+        assert y.shape == (nch, w.shape[1]), (i, y.shape, w.shape)
+        assert nerr(y[:2].cpu().numpy(), w) <= 1e-5, (i, nerr(y[:2].cpu().numpy(), w))
+        assert states_equal(f, o), i
+        a += n
+
+
 def test_repeated_one_shot_calls_reuse_a_reset_handle(rng):
     """filt(h, x, ratio) keeps the handle of a one-shot call and resets it when the same taps / ratio / layout come again:
     the repeated call must equal a fresh filter's output bit for bit (mrb_reset is a full re-initialisation), for host and
