@@ -1,6 +1,7 @@
 """Host logic of the library on a host-only handle (device = -1): counts, phase sequencing and carried
 state must be EXACT against the oracle for every kernel type and any chunking.  CPU only."""
 import ctypes as C
+import math
 from fractions import Fraction
 
 import numpy as np
@@ -229,3 +230,51 @@ def test_schedule_bit_exact_against_the_oracle_loops(args, rng):
             assert np.array_equal(pb, np.asarray(sched[1], dtype=np.int64) - 1)
             if len(args) == 2:                                   # arbitrary: alpha
                 assert np.array_equal(pa, np.asarray(sched[2], dtype=np.float64))
+
+
+def _literal_replay(acc, x_idx, delta, nphi, n_in):
+    """The reference's update (src/Filters.jl:663-673), literally, in Python floats: (n, acc) per output and the end state."""
+    ns, accs = [], []
+    while x_idx <= n_in:
+        ns.append(x_idx - 1)
+        accs.append(acc)
+        acc += delta
+        if acc > nphi:
+            x_idx += int(math.floor((acc - 1) / nphi))
+            acc = math.fmod(acc - 1, nphi) + 1
+    return np.asarray(ns, np.int64), np.asarray(accs, np.float64), acc, x_idx
+
+
+def test_replay_equals_the_literal_recurrence_for_random_rates(rng):
+    """mrb_seq.h ArbStepper (one add and one exact subtract per update, a guard band for the rounded quotient) against the
+    literal floating-point update of the reference: random rates from steep decimation to high interpolation, random branch
+    counts and start accumulators set by the caller, output by output and bit for bit."""
+    h = rng.random(64)
+    cases = [(0.918734, 32), (1.37, 32), (0.5000001, 32), (0.51, 7), (15.9, 32), (1.0, 32), (2.0, 32), (1 / 3.0, 5), (40.0, 32)]
+    for _ in range(40):
+        nphi = int(rng.integers(1, 70))
+        cases.append((float(np.exp(rng.uniform(np.log(0.3), np.log(nphi + 3.0)))), nphi))
+    for rate, nphi in cases:
+        f = mr.FIRFilter(h, rate, nphi, nchannels=1, sample_dtype=np.float64, device=-1)
+        delta = nphi / rate
+        acc, x_idx = 1.0, 1
+        for j, n_in in enumerate([3, 5000, 1, 12000, 64, 9000]):
+            if j == 3:                                              # an accumulator the caller set: not on any grid
+                s = f._get_state()
+                acc = float(rng.uniform(1.0, nphi + 1.0))
+                s.phi_accumulator = acc
+                s.phi_idx, s.alpha = int(acc), acc - int(acc)
+                f._set_state(s)
+                x_idx = s.input_deficit
+            pn, pb, pa = product_schedule(f, n_in)
+            wn, wacc, acc, x_idx = _literal_replay(acc, x_idx, delta, float(nphi), n_in)
+            assert len(pn) == len(wn), (rate, nphi, j)
+            assert np.array_equal(pn, wn), (rate, nphi, j)
+            if len(wn) > 1:                                         # (output 0 carries the stored (phi, alpha) pair)
+                wphi = np.floor(wacc[1:]).astype(np.int64)
+                assert np.array_equal(pb[1:], wphi - 1), (rate, nphi, j)
+                assert np.array_equal(pa[1:], wacc[1:] - wphi), (rate, nphi, j)
+            assert advance(f, n_in) == len(wn)
+            s = f._get_state()
+            x_idx -= n_in                                           # the carried deficit (src/Filters.jl:734)
+            assert s.phi_accumulator == acc and s.input_deficit == x_idx, (rate, nphi, j, s.phi_accumulator, acc)
