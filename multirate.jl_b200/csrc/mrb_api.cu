@@ -1034,6 +1034,7 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 if (mma_int && !unit_better) {
                     MmaSched S{};
                     S.mode = 2; S.L = f->L; S.M = f->M; S.p0 = P.p0; S.d0m1 = P.d0m1; S.k_base = 0; S.cplx = cx ? 1 : 0;
+                    S.span_c = (15 * f->M) / f->L + 1;
                     GenParams Pv = P;
                     if (cx) { Pv.ldx *= 2; Pv.n_in *= 2; Pv.H *= 2; Pv.ldy *= 2; }
                     // widest spread of window starts in a group: 32 outputs, or 16 complex outputs seen as 32 floats
@@ -1123,7 +1124,7 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                         MmaSched S{};
                         S.mode = f->kind == MRB_FARROW ? 1 : 0; S.sn = s.d_n; S.sphi = s.d_phi; S.sa = s.d_a; S.cplx = cx ? 1 : 0;
                         GenParams Pv = P;
-                        if (cx) { Pv.ldx *= 2; Pv.n_in *= 2; Pv.H *= 2; Pv.ldy *= 2; gs32 = 2 * gs32 + 1; }
+                        if (cx) { Pv.ldx *= 2; Pv.n_in *= 2; Pv.H *= 2; Pv.ldy *= 2; S.span_c = gs32; gs32 = 2 * gs32 + 1; }
                         kb = mma_try_launch(f->mma, tc.mrows, Pv, S, f->polyorder + 1, f->d_bank, f->d_dbank, f->d_pnfb, cx ? 2 * k0 : k0,
                                             cx ? 2 * cnt : cnt, gs32, st, &f->last_kernel, &f->launches, tag);
                         if (cx && kb > 0) kb /= 2;

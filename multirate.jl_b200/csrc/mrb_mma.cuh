@@ -79,6 +79,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
                  "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -110,11 +114,12 @@ struct MmaSched {               // where the pre-pass takes an output's (window 
     // is output k's part b: its window ends at float 2 n_k + b and holds tap i of the branch at window position 2i (the odd
     // positions -- the other part's samples -- are zeros): a real FIR of 2T - 1 taps with the schedule below.  Same bytes per
     // float as the real kernel, twice the MMAs per output (the pipe has the room: 26 % active on the float32 resampler).
-    int cplx;
+    int cplx;                   // 0 real; 1 complex64 on the float view (above); 2 complex64 SPLIT (below, k_mma_fir)
+    long long span_c;           // cplx: widest spread of window starts inside a group of 16 outputs, in complex samples
 };
 
 __device__ __forceinline__ void mma_sched_at(const MmaSched &S, int64_t kf, int64_t &n, int64_t &phi) {
-    const int64_t k = S.cplx ? kf >> 1 : kf;                           // output index (kf: float index of the interleaved view)
+    const int64_t k = S.cplx == 1 ? kf >> 1 : kf;                      // output index (kf: float index of the interleaved view)
     if (S.mode == 2) {
         const long long t = S.p0 + (S.k_base + k) * S.M;
         const long long q = t / S.L;
@@ -124,7 +129,7 @@ __device__ __forceinline__ void mma_sched_at(const MmaSched &S, int64_t kf, int6
         n = S.sn[k];
         phi = S.mode == 0 ? S.sphi[k] : 0;
     }
-    if (S.cplx) n = 2 * n + (kf & 1);
+    if (S.cplx == 1) n = 2 * n + (kf & 1);
 }
 
 // Rows [0, nrows) of the tile table (nrows = tiles * G; for periodic integer schedules only one period of tiles is
@@ -134,11 +139,13 @@ __global__ void __launch_bounds__(256)
 k_mma_tiles(const float *__restrict__ pfb, const float *__restrict__ dpfb, const double *__restrict__ pnfb, int P1, int T, int KB,
             const MmaSched S, int64_t H, int64_t nout, int64_t nrows, int64_t ngroups, float *__restrict__ tiles,
             int32_t *__restrict__ gstart) {
+    // split complex mode: a group is 16 (complex) outputs, the tile keeps its 32-row layout with rows 16..31 unused
+    const int OG = S.cplx == 2 ? G / 2 : G;
     {   // window starts: one thread per group
         const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
         if (g < ngroups) {
             int64_t n, phi;
-            mma_sched_at(S, g * G, n, phi);
+            mma_sched_at(S, g * OG, n, phi);
             const int64_t xg = n - H;
             gstart[g] = (int32_t)(xg >= 0 ? (xg & ~(int64_t)7) : -(((-xg) + 7) & ~(int64_t)7));
         }
@@ -149,23 +156,24 @@ k_mma_tiles(const float *__restrict__ pfb, const float *__restrict__ dpfb, const
     const int64_t g = k / G;
     const int r = (int)(k - g * G);
     int64_t ng0, phig;
-    mma_sched_at(S, g * G, ng0, phig);
+    mma_sched_at(S, g * OG, ng0, phig);
     const int64_t xg = ng0 - H;
     const int64_t al = xg >= 0 ? (xg & ~(int64_t)7) : -(((-xg) + 7) & ~(int64_t)7);
-    const bool live = k < nout;
+    const int64_t ko = g * OG + r;                                   // output this row belongs to
+    const bool live = r < OG && ko < nout;
     int64_t nk = 0, phik = 0;
-    if (live) mma_sched_at(S, k, nk, phik);
+    if (live) mma_sched_at(S, ko, nk, phik);
     const int d = live ? (int)(nk - H - al) : 0;
-    const double ph = live && S.mode != 2 ? S.sa[S.cplx ? k >> 1 : k] : 0.0;   // farrow: phase; arbitrary: alpha
-    const int Tw = S.cplx ? 2 * T - 1 : T;                           // window length in elements of the (float) view
+    const double ph = live && S.mode != 2 ? S.sa[S.cplx == 1 ? ko >> 1 : ko] : 0.0;   // farrow: phase; arbitrary: alpha
+    const int Tw = S.cplx == 1 ? 2 * T - 1 : T;                      // window length in elements of the view
     const int64_t obase = phik * T;
     const int64_t tile_floats = (int64_t)2 * KB * G * 32;
     float *th = tiles + g * tile_floats, *tl = th + (int64_t)KB * G * 32;
     for (int j = lane; j < KB * 32; j += 32) {
         const int iw = j - d;                                        // window position
-        const int i = S.cplx ? iw >> 1 : iw;                         // tap (complex view: taps sit at the even positions)
+        const int i = S.cplx == 1 ? iw >> 1 : iw;                    // tap (float view: taps sit at the even positions)
         float v = 0.f;
-        if (live && iw >= 0 && iw < Tw && !(S.cplx && (iw & 1))) {
+        if (live && iw >= 0 && iw < Tw && !(S.cplx == 1 && (iw & 1))) {
             if (S.mode == 1) {
                 // currentTaps[i] = polyval(pnfb[i], phase): Horner highest order first in Float64, separately rounded
                 // multiply and add, rounded to the tap type (src/Filters.jl:789-791)
@@ -200,6 +208,11 @@ struct alignas(16) MmaParams {
     int nissue;                // 2: a look-ahead warp does the issuer's waits (default); 1: the issuer waits itself (MRB_MMA_ISSUERS=1)
     int period;                // tile of group g = tile (g mod period): g_end - 0 for aperiodic tables
     int resident;              // period <= NWB: every tile is loaded once and stays in its slot
+    int split;                 // 1: complex64 SPLIT mode.  Samples arrive as float boxes (re, im interleaved; 16 complex samples per box);
+                               // the converters put the real parts and the imaginary parts into SEPARATE tensor-memory rings (16 columns
+                               // per box each), so a group of 16 complex outputs is two N = 16 products with the SAME tap tile -- D_re =
+                               // A_re W, D_im = A_im W -- instead of one N = 32 product on the float view whose tile is half zeros.  All
+                               // window indices (gstart, KS, H) are in complex samples; the epilogue interleaves re / im again.
     int fwd;                   // 1: the epilogue releases tile slots and ring boxes once it sees the group's accumulators complete
                                // (one tcgen05.commit per group instead of three or four on the issuing thread); 0: MRB_MMA_FWD=0
     int nch;                   // channels (rows past it read zero history)
@@ -241,6 +254,27 @@ __device__ __forceinline__ void mma_issue_group(uint32_t d, uint32_t a_hi, uint3
     }
 }
 
+// split complex mode: per K-step the same two tile halves serve the real-part ring and the imaginary-part ring (N = 16 each)
+template <int G, int KS>
+__device__ __forceinline__ void mma_issue_group_split(uint32_t d, uint32_t a_hi, uint32_t a_lo, int col0, uint64_t bh0, uint32_t lo_off,
+                                                      uint32_t idesc) {
+    constexpr int RCS = kMmaNAB * 16;                                  // columns of one part's ring
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        int col = col0 + 8 * ks;
+        col -= col >= RCS ? RCS : 0;
+        const uint64_t bh = bh0 + (uint64_t)(((uint32_t)((ks >> 2) * G * 128 + (ks & 3) * 32)) >> 4);
+        const uint64_t bl = bh + lo_off;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {                         // 0: real parts, 1: imaginary parts
+            const uint32_t dp = d + (uint32_t)(part * 16), c = (uint32_t)(part * RCS + col);
+            umma_ts_tf32(dp, a_hi + c, bh, idesc, ks > 0 ? 1u : 0u);
+            umma_ts_tf32(dp, a_hi + c, bl, idesc, 1u);
+            umma_ts_tf32(dp, a_lo + c, bh, idesc, 1u);
+        }
+    }
+}
+
 // mbarrier wait that adds the cycles it spent to `acc` when profiling is on
 __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bool prof, long long &acc) {
     if (!prof) { mbar_wait(bar, parity); return; }
@@ -249,7 +283,7 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
     acc += clock64() - t0;
 }
 
-template <int G>
+template <int G, bool SPLIT>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const float *__restrict__ tiles,
           const int32_t *__restrict__ gstart, const __grid_constant__ MmaParams P) {
@@ -319,9 +353,11 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
     // sample index of box 0 of the tile.  It is negative for the tile that holds the chunk's first outputs, whose windows
     // reach into the history: boxes j < jneg lie wholly before x[0]; the converters fill them from the history buffer
     // (shiftin!'s carry, src/support.jl:61-80) instead of a TMA box, so no separate head kernel is needed.
-    const int xbase = gs[0] & ~(kMmaBox - 1);
-    const int jneg = xbase < 0 ? (-xbase) / kMmaBox : 0;
-    const int jlast = (gs[ng - 1] - xbase + P.KS * 8 - 1) / kMmaBox;   // newest box the tile reads
+    constexpr int BW = SPLIT ? kMmaBox / 2 : kMmaBox;                  // window samples (= ring columns) per box
+    constexpr int BS = SPLIT ? 4 : 5;                                  // log2(BW)
+    const int xbase = gs[0] & ~(BW - 1);
+    const int jneg = xbase < 0 ? (-xbase) >> BS : 0;
+    const int jlast = (gs[ng - 1] - xbase + P.KS * 8 - 1) >> BS;       // newest box the tile reads
 
     if (warp == 8) {
         // ---------------- x loader: TMA boxes into the shared-memory ring
@@ -330,7 +366,7 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
                 const int s = jx % NXB;
                 if (jx >= NXB) mbar_wait_prof(B_XEMPTY(s), (uint32_t)((jx / NXB - 1) & 1), prof, c0);
                 mbar_expect_tx(B_XFULL(s), kMmaBoxBytes);
-                tma_load_2d(smem_u32(xring) + (uint32_t)(s * kMmaBoxBytes), &tmx, xbase + (jx + jneg) * kMmaBox, ch0, B_XFULL(s));
+                tma_load_2d(smem_u32(xring) + (uint32_t)(s * kMmaBoxBytes), &tmx, (xbase + (jx + jneg) * BW) * (SPLIT ? 2 : 1), ch0, B_XFULL(s));
             }
             if (prof) pr[0] = c0;
         }
@@ -370,7 +406,7 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
             const int ws_wrap = P.resident ? P.period : P.NWB;
             int ws = P.resident ? (int)(g0 % P.period) : 0;
             for (int w = 0; w < ng; ++w) {
-                const int need = (gs[w] - xbase + P.KS * 8 - 1) / kMmaBox;
+                const int need = (gs[w] - xbase + P.KS * 8 - 1) >> BS;
                 for (; boxes_ready <= need; ++boxes_ready) {
                     mbar_wait(B_AFULL(ar_slot), ar_par);
                     if (++ar_slot == NAB) { ar_slot = 0; ar_par ^= 1u; }
@@ -387,7 +423,7 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
     } else if (warp == 10) {
         // ---------------- MMA issuer (one elected lane)
         const bool ahead = P.nissue == 2;                              // the waits are done by the look-ahead warp
-        const uint32_t idesc = umma_idesc_tf32(kMmaRows, G);
+        const uint32_t idesc = umma_idesc_tf32(kMmaRows, SPLIT ? G / 2 : G);
         const uint32_t lo_off = (uint32_t)(P.KB * G * 128) >> 4;       // hi -> lo half of a tile, in descriptor units
         int boxes_ready = 0, dead = 0;
         int ar_slot = 0;                                               // a_full slot of box `boxes_ready` and its phase parity
@@ -398,9 +434,9 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
         long long c4 = 0;
         for (int w = 0; w < ng; ++w) {
             const int a0 = gs[w] - xbase;                              // multiple of 8
-            const int need = (a0 + P.KS * 8 - 1) / kMmaBox;
+            const int need = (a0 + P.KS * 8 - 1) >> BS;
             // ring boxes no later group reads: everything before the next group's first box
-            const int next_first = w + 1 < ng ? (gs[w + 1] - xbase) / kMmaBox : jlast + 1;
+            const int next_first = w + 1 < ng ? (gs[w + 1] - xbase) >> BS : jlast + 1;
             if (ahead) {
                 mbar_wait_prof(B_GO(w & 3), (uint32_t)((w >> 2) & 1), prof, c0);
             } else {
@@ -416,10 +452,26 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
             if (prof) c4 += clock64() - tf0;
             const uint32_t d = tb + (uint32_t)(C::TM_D + (w & 1) * G);
             const uint64_t bh0 = umma_desc_sw128(smem_u32(wring) + (uint32_t)(ws * P.tile_bytes));
-            const int col0 = a0 % kMmaRC;
+            const int col0 = SPLIT ? a0 % (NAB * 16) : a0 % kMmaRC;   // (constant divisors)
             const long long ti0 = prof ? clock64() : 0;
             if (elect_one()) {
                 const uint32_t ah = tb + (uint32_t)C::TM_AH, al = tb + (uint32_t)C::TM_AL;
+                if constexpr (SPLIT) {
+                    switch (P.KS) {                                      // (the host admits K <= 96 complex columns: 12 K-steps)
+                    case 1: mma_issue_group_split<G, 1>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    case 2: mma_issue_group_split<G, 2>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    case 3: mma_issue_group_split<G, 3>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    case 4: mma_issue_group_split<G, 4>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    case 5: mma_issue_group_split<G, 5>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    case 6: mma_issue_group_split<G, 6>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    case 7: mma_issue_group_split<G, 7>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    case 8: mma_issue_group_split<G, 8>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    case 9: mma_issue_group_split<G, 9>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    case 10: mma_issue_group_split<G, 10>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    case 11: mma_issue_group_split<G, 11>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    default: mma_issue_group_split<G, 12>(d, ah, al, col0, bh0, lo_off, idesc); break;
+                    }
+                } else
                 switch (P.KS) {                                          // compile-time trip counts: straight-line issue code
                 case 1: mma_issue_group<G, 1>(d, ah, al, col0, bh0, lo_off, idesc); break;
                 case 2: mma_issue_group<G, 2>(d, ah, al, col0, bh0, lo_off, idesc); break;
@@ -467,7 +519,7 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
         const uint32_t lanebase = tb + ((uint32_t)(q * 32) << 16);
         const uint32_t rowpart = ((uint32_t)row * 128u) ^ (((uint32_t)row & 7u) << 4);     // SWIZZLE_128B
         const bool rowlive = ch0 + row < P.nch;
-        const float *hrow = P.hist + (long long)(ch0 + row) * P.H;
+        const float *hrow = P.hist + (long long)(ch0 + row) * P.H * (SPLIT ? 2 : 1);   // (split: P.H counts complex samples)
         for (int j = 0; j <= jlast; ++j) {
             const int jx = j - jneg;                                   // >= 0: box jx of the x ring; < 0: a history box
             const int s = jx >= 0 ? jx % NXB : 0, as = j % NAB;
@@ -489,11 +541,20 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
                     }
                 } else {
                     // samples n = xbase + 32 j + 16 hlf + e < 0: ext index H + n of [history | x]; zero before the history
-                    const int n0 = xbase + j * kMmaBox + hlf * 16;
+                    if constexpr (SPLIT) {                                     // float e of the half box = part e & 1 of complex sample n0 + e / 2
+                        const int n0 = xbase + j * BW + hlf * 8;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const long long hi = P.H + n0 + e;
-                        x[e] = (rowlive && hi >= 0) ? __ldg(hrow + hi) : 0.f;
+                        for (int e = 0; e < 16; ++e) {
+                            const long long hi = P.H + n0 + (e >> 1);
+                            x[e] = (rowlive && hi >= 0) ? __ldg(hrow + 2 * hi + (e & 1)) : 0.f;
+                        }
+                    } else {
+                        const int n0 = xbase + j * kMmaBox + hlf * 16;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const long long hi = P.H + n0 + e;
+                            x[e] = (rowlive && hi >= 0) ? __ldg(hrow + hi) : 0.f;
+                        }
                     }
                 }
                 uint32_t vh[16], vl[16];
@@ -503,8 +564,20 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
                     vh[e] = __float_as_uint(h);
                     vl[e] = __float_as_uint(tf32_rna(x[e] - h));
                 }
-                tmem_st16(lanebase + (uint32_t)(C::TM_AH + as * kMmaBox + hlf * 16), vh);
-                tmem_st16(lanebase + (uint32_t)(C::TM_AL + as * kMmaBox + hlf * 16), vl);
+                if constexpr (SPLIT) {
+                    // real parts -> columns [0, 112) of each ring, imaginary parts -> [112, 224): 8 complex samples per half box
+                    uint32_t rh[8], ih[8], rl[8], il[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { rh[e] = vh[2 * e]; ih[e] = vh[2 * e + 1]; rl[e] = vl[2 * e]; il[e] = vl[2 * e + 1]; }
+                    const uint32_t cc = (uint32_t)(as * 16 + hlf * 8);
+                    tmem_st8(lanebase + (uint32_t)C::TM_AH + cc, rh);
+                    tmem_st8(lanebase + (uint32_t)C::TM_AH + (uint32_t)(NAB * 16) + cc, ih);
+                    tmem_st8(lanebase + (uint32_t)C::TM_AL + cc, rl);
+                    tmem_st8(lanebase + (uint32_t)C::TM_AL + (uint32_t)(NAB * 16) + cc, il);
+                } else {
+                    tmem_st16(lanebase + (uint32_t)(C::TM_AH + as * kMmaBox + hlf * 16), vh);
+                    tmem_st16(lanebase + (uint32_t)(C::TM_AL + as * kMmaBox + hlf * 16), vl);
+                }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
@@ -524,7 +597,7 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
             if (P.fwd && tid == 32) {
                 // every MMA of group w has completed: its tile slot and the ring boxes before the next group's window are free
                 if (!P.resident) { mbar_arrive(B_WEMPTY(ws_e)); if (++ws_e == P.NWB) ws_e = 0; }
-                const int next_first = w + 1 < ng ? (gs[w + 1] - xbase) / kMmaBox : jlast + 1;
+                const int next_first = w + 1 < ng ? (gs[w + 1] - xbase) >> BS : jlast + 1;
                 for (int b = dead_e; b < next_first; ++b) mbar_arrive(B_AEMPTY(b % NAB));
                 if (next_first > dead_e) dead_e = next_first;
             }
@@ -534,6 +607,13 @@ k_mma_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(B_DEMPTY(w & 1));
+            if constexpr (SPLIT) {                                             // columns 0..15 real parts, 16..31 imaginary parts -> interleaved
+                uint32_t t[G];
+#pragma unroll
+                for (int i = 0; i < G / 2; ++i) { t[2 * i] = v[i]; t[2 * i + 1] = v[G / 2 + i]; }
+#pragma unroll
+                for (int i = 0; i < G; ++i) v[i] = t[i];
+            }
             // the staging buffer of group w-2 must have been read by its TMA store
             if (tid == 0) {
                 const long long t0 = prof ? clock64() : 0;
@@ -611,7 +691,9 @@ static inline int32_t mma_prepare(MmaPlan &p, int kind, int tx, int ty, int th, 
     p.num_sms = prop.multiProcessorCount;
     p.T = (int)T;
     p.max_smem = (int)prop.sharedMemPerBlockOptin;
-    e = cudaFuncSetAttribute(k_mma_fir<kMmaG>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.max_smem);
+    e = cudaFuncSetAttribute(k_mma_fir<kMmaG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.max_smem);
+    if (e != cudaSuccess) return (int32_t)e;
+    e = cudaFuncSetAttribute(k_mma_fir<kMmaG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.max_smem);
     if (e != cudaSuccess) return (int32_t)e;
     p.ok = true;
     return 0;
@@ -632,7 +714,7 @@ static inline cudaError_t mma_reserve(MmaRows &r, int64_t ntiles, int64_t groups
 // arrays for the arbitrary-rate kinds, the closed form for the integer kinds); max_group_span = widest spread of window
 // starts inside a group of kMmaG outputs.  Builds the tap tiles, then launches the main kernel for the whole slice
 // (chunk head included).  Returns 0 (the first output covered), -1 when not covered, -2 on a CUDA error.
-static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G, const MmaSched &S, int P1,
+static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G, const MmaSched &S_in, int P1,
                                      const void *d_pfb, const void *d_dpfb, const double *d_pnfb, int64_t y0, int64_t cnt,
                                      int64_t max_group_span, cudaStream_t st, const char **name, int64_t *launches, uint64_t tag = 0) {
     static const bool trace = getenv("MRB_TRACE") != nullptr;
@@ -645,7 +727,13 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     // a CTA is 128 channels wide (UMMA M): with a handful of channels the other kernels win (README benchmark, ONE channel:
     // k_stream 0.024 ms, this kernel 0.19 ms)
     if (G.nch < 48) MRB_MMA_SKIP("too few channels for a 128-row tile");
-    const int64_t Tw = S.cplx ? 2 * (int64_t)p.T - 1 : p.T;           // window length in elements of the view
+    // complex64: the SPLIT form (real and imaginary parts in separate tensor-memory rings of 7 x 16 columns, half the MMA work)
+    // when a group's window fits 96 complex columns, else the float view (cplx = 1)
+    static const bool no_split = getenv("MRB_MMA_SPLIT") && atoi(getenv("MRB_MMA_SPLIT")) == 0;
+    MmaSched S = S_in;
+    const bool split = S.cplx == 1 && !no_split && (int64_t)p.T + 7 + S.span_c <= 96;
+    if (split) { S.cplx = 2; max_group_span = S.span_c; }
+    const int64_t Tw = S.cplx == 1 ? 2 * (int64_t)p.T - 1 : p.T;      // window length in elements of the view
     const int64_t kneed = Tw + 7 + max_group_span;                    // samples a group's window spans at worst
     const int KB = (int)ceil_div(kneed, 32);
     if (KB > kMmaMaxKB) MRB_MMA_SKIP("window group wider than the tensor-memory ring");
@@ -664,7 +752,7 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     // interpolators: ONE tile, kept resident in shared memory; 147//160: 147 tiles, L2 resident).
     int64_t period = groups;
     if (S.mode == 2) {
-        const int64_t og = S.cplx ? GG / 2 : GG, adv = S.cplx ? 2 : 1;       // outputs per group; view elements per input sample
+        const int64_t og = S.cplx ? GG / 2 : GG, adv = S.cplx == 1 ? 2 : 1;  // outputs per group; view elements per input sample
         for (int64_t q = 1; q <= std::min<int64_t>(groups, 16 * S.L); ++q)
             if ((q * og * S.M) % S.L == 0 && (((q * og * S.M) / S.L) * adv) % 8 == 0) { period = q; break; }
     }
@@ -685,9 +773,10 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
     P.period = (int)ntiles; P.resident = resident ? 1 : 0;
     static const int fwd = getenv("MRB_MMA_FWD") && atoi(getenv("MRB_MMA_FWD")) == 0 ? 0 : 1;
     P.fwd = fwd;
+    P.split = split ? 1 : 0;
     static const int n_issuers = getenv("MRB_MMA_ISSUERS") && atoi(getenv("MRB_MMA_ISSUERS")) == 1 ? 1 : 2;
     P.nissue = n_issuers;
-    P.nch = (int)G.nch; P.hist = static_cast<const float *>(G.hist); P.H = G.H;
+    P.nch = (int)G.nch; P.hist = static_cast<const float *>(G.hist); P.H = split ? G.H / 2 : G.H;   // (G is the float view)
     const int64_t span = groups - g_begin;
     const int64_t cgroups = ceil_div(G.nch, kMmaRows);
     // time tiles: one CTA per SM (shared and tensor memory), so the grid should be whole waves of num_sms CTAs: take the
@@ -730,15 +819,17 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
         rw.tag = tag;
         const int64_t nrows = ntiles * GG;
         const unsigned gb = (unsigned)std::max(ceil_div(nrows, 8), ceil_div(groups, 256));
-        k_mma_tiles<GG><<<gb, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, KB, S, G.H,
-                                            S.mode == 2 ? nrows : cnt, nrows, groups, rw.d_tiles, rw.d_gstart);
+        const int64_t outs = split ? (S.mode == 2 ? ntiles * (GG / 2) : cnt / 2) : (S.mode == 2 ? nrows : cnt);
+        k_mma_tiles<GG><<<gb, 256, 0, st>>>((const float *)d_pfb, (const float *)d_dpfb, d_pnfb, P1, p.T, KB, S, split ? G.H / 2 : G.H,
+                                            outs, nrows, groups, rw.d_tiles, rw.d_gstart);
         ++*launches;
         if (trace && cudaPeekAtLastError() != cudaSuccess)
             fprintf(stderr, "[mrb] k_mma_tiles failed: %s (mode %d cnt %lld groups %lld ntiles %lld KB %d)\n", cudaGetErrorString(cudaPeekAtLastError()),
                     S.mode, (long long)cnt, (long long)groups, (long long)ntiles, KB);
     }
     dim3 grid((unsigned)cgroups, (unsigned)tiles);
-    k_mma_fir<GG><<<grid, kMmaThreads, fixed + nwb * tile_bytes, st>>>(tmx, tmy, rw.d_tiles, rw.d_gstart, P);
+    if (split) k_mma_fir<GG, true><<<grid, kMmaThreads, fixed + nwb * tile_bytes, st>>>(tmx, tmy, rw.d_tiles, rw.d_gstart, P);
+    else k_mma_fir<GG, false><<<grid, kMmaThreads, fixed + nwb * tile_bytes, st>>>(tmx, tmy, rw.d_tiles, rw.d_gstart, P);
     if (cudaPeekAtLastError() != cudaSuccess) {
         if (trace)
             fprintf(stderr, "[mrb] k_mma_fir failed: %s (mode %d cnt %lld y0 %lld n_in %lld nch %lld groups %lld tiles %lld GT %d KB %d KS %d NWB %d period %d resident %d span %lld H %lld)\n",
@@ -760,7 +851,7 @@ static inline int64_t mma_try_launch(MmaPlan &p, MmaRows &rw, const GenParams &G
                     (long long)(cgroups * tiles), s[9], s[10], s[0], s[1], s[2], s[3], s[4], s[15], s[11], s[14], s[5], s[6], s[13], s[7], s[8], s[12]);
         }
     }
-    *name = S.cplx ? (resident ? "mma_c64_g32_resident" : "mma_c64_g32") : (resident ? "mma_f32_g32_resident" : "mma_f32_g32");
+    *name = S.cplx == 2 ? (resident ? "mma_c64_split_resident" : "mma_c64_split") : S.cplx ? (resident ? "mma_c64_g32_resident" : "mma_c64_g32") : (resident ? "mma_f32_g32_resident" : "mma_f32_g32");
     ++*launches;
     return k_begin;
 }

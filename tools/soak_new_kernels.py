@@ -14,6 +14,8 @@ cases = {
     "c4a64": (0.918734, (mo.firdes(hl, 0.45, beta, samplerate=32) * N).astype(np.float64), 1024, (N,), torch.float64, "table_f64_dmma"),
     "c4f64": (0.918734, (mo.firdes(hl, 0.45, beta, samplerate=32) * N).astype(np.float64), 1024, (N, 4), torch.float64, "table_f64_dmma"),
     "c2": (Fraction(1, 8), mo.firdes(256, 0.5 / 8, 7.8562).astype(np.float32), 1024, (), torch.complex64, "decim8_c64"),
+    "c5": (Fraction(147, 160), mo.firdes(3528, 0.5 / 147, 7.8562).astype(np.float32), 2048, (), torch.complex64, "mma_c64_split"),
+    "x4ac": (0.918734, (mo.firdes(hl, 0.45, beta, samplerate=32) * N).astype(np.float32), 1024, (N,), torch.complex64, "mma_c64_g32"),
 }
 torch.manual_seed(7)
 for name, (ratio, h, nch, extra, dt, want) in cases.items():
