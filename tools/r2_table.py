@@ -11,7 +11,7 @@ s = open(p).read()
 a = s.index("| **C5** rational 147//160 c64, 8192 ch (headline)")
 b = s.index("Earlier runs of the same command on other boxes are kept")
 rows = []
-rows.append("| **C5** rational 147//160 c64, 8192 ch (headline) | **`k_mma_fir` on the float view** (`%s`) | **%.1f** | %.3f | HBM **%.3f** | %.3f | %.2f | 308.4 (`k_tiled_c64`, now the CUDA-core arm: 311) |" % (d["roofline"]["kernel"], d["value"] / 1e3, d["roofline"]["kernel_ms"], d["roofline"]["frac"], d["roofline"]["frac"], d["e2e"]["value"] / 1e3))
+rows.append("| **C5** rational 147//160 c64, 8192 ch (headline) | **`k_mma_fir<32, split>`** (`%s`) | **%.1f** | %.3f | HBM **%.3f** | %.3f | %.2f | 308.4 (`k_tiled_c64`, now the CUDA-core arm: 311) |" % (d["roofline"]["kernel"], d["value"] / 1e3, d["roofline"]["kernel_ms"], d["roofline"]["frac"], d["roofline"]["frac"], d["e2e"]["value"] / 1e3))
 v = row("c1"); rows.append("| C1 README one-shot shape, 1 ch f32, 1e6 | `k_stream` (1 channel is below the tensor-core kernel's 48-channel floor) | %.1f | %.3f | latency | — | %.1f | 24.0 |" % (v[0], v[1], v[4]))
 v = row("c2"); rows.append("| C2 decimator 1//8 × 256, 1024 ch c64 | **`k_decim8`** (lane per channel, launch-constant taps) | **%.1f** | %.3f | FP32 **%.3f** | %.2f | %.2f (H2D alone: 8 input bytes per output byte) | 34.3 |" % (v[0], v[1], v[2], v[3], v[4]))
 v = row("c3a"); rows.append("| C3a interpolator 4//1 × 128, 4096 ch f32 | **`k_mma_fir` (resident tile)** | **%.1f** | %.3f | HBM **%.2f** | %.2f | %.1f | 857.9 |" % (v[0], v[1], v[2], v[3], v[4]))
