@@ -1027,9 +1027,12 @@ static int32_t run_channels(mrb_filter *f, const void *x, int64_t ldx, int64_t n
                 // short single-rate filters are HBM bound on the CUDA cores already (standard, 32 taps: k_unit_f32 730 Gout/s,
                 // tensor-core kernel 592); from ~48 taps on the tensor cores win (128 taps: 438 against 227)
                 const bool cx = f->mma.cplx != 0;                  // complex64: the kernel runs on the float view of x, y, history
-                // complex64 (measured): rational 147//160 326.7 against 310.7 on k_tiled_c64, 160//147 355 against 286; the unit
-                // kernel keeps standard / interpolator L in {1,2,4} (4//1: 434 against 407), k_decim / k_decim8 the decimators
-                const bool unit_better = cx ? (f->unit.ok || (f->kind == MRB_DECIMATOR && f->decim.ok))
+                // complex64 (measured, split form): rational 147//160 345 against 311 on k_tiled_c64, 160//147 357 against 286,
+                // interpolator 4//1 495 against 431 on k_unit_c64, standard x 64 taps 338 against 165; short standard filters stay
+                // on the tiled / unit kernels, decimators on k_decim / k_decim8 (MRB_C64_UNIT_FIRST=1: the unit kernel first)
+                static const bool cx_unit_first = getenv("MRB_C64_UNIT_FIRST") != nullptr;
+                const bool unit_better = cx ? ((cx_unit_first && f->unit.ok) || (f->unit.ok && f->L == 1 && f->M == 1 && f->T <= 24) ||
+                                               (f->kind == MRB_DECIMATOR && f->decim.ok))
                                             : (f->unit.ok && f->L == 1 && f->M == 1 && f->T <= 48);
                 if (mma_int && !unit_better) {
                     MmaSched S{};

@@ -793,13 +793,16 @@ def test_fast_paths_random_stress_against_generic_kernel(rng):
         while math.gcd(L, M) != 1 or L == M:
             L = int(r.integers(M // 2 + 1, 2 * M))
         cases.append((Fraction(L, M), int(r.integers(1, 40 * L + 1)), np.complex64, "mma_c64"))
+    for _ in range(4):                                             # tensor cores, split mode: complex64 standard / interpolator
+        L = int(r.choice([1, 2, 3, 4, 7]))
+        cases.append((Fraction(L, 1), int(r.integers(25 * L, 70 * L + 1)), np.complex64, "mma_c64"))
     for ratio, ntaps, tx, want in cases:
         h = r.standard_normal(ntaps).astype(np.float32)
         nch = int(r.integers(48, 200)) if want == "mma_c64" else int(r.integers(1, 200))
         n = 4 * int(r.integers(1500, 3000))
         x = torch.from_numpy(rand_samples(r, (nch, n), tx)).cuda()
         f = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
-        if want in ("unit", "decim_f32", "tiled"):
+        if want in ("unit", "unit_c64", "decim_f32", "tiled"):
             f.set_kernel_policy(2)                                 # keep to the CUDA-core fast paths here (tensor cores: below)
         g = mr.FIRFilter(h, ratio, nchannels=nch, sample_dtype=tx)
         g.set_kernel_policy(1)
