@@ -343,10 +343,33 @@ function filt!(y::DeviceMatrix{Tb}, f::FIRFilter, x::DeviceMatrix{Tx}; stream::P
     Int(n[])
 end
 
-# one-shot forms, src/Filters.jl:858-873
-filt(h::Vector, x::VecOrMat, ratio::Rational = 1//1) = filt(FIRFilter(h, ratio), x)
-filt(h::Vector, x::VecOrMat, rate::AbstractFloat, Nϕ::Integer = 32) = filt(FIRFilter(h, rate, Nϕ), x)
-filt(h::Vector, x::VecOrMat, rate::AbstractFloat, Nϕ::Integer, polyorder::Integer) = filt(FIRFilter(h, rate, Nϕ, polyorder), x)
+# one-shot forms, src/Filters.jl:858-873.  Building a filter costs device allocations, a stream and the plan tables (milliseconds
+# around a 0.03 ms kernel at the README's benchmark shape), so the filters of recent one-shot calls are kept per task and RESET
+# (mrb_reset is a full re-initialisation) when the same taps / ratio / input layout come again -- the Python twin does the same
+# (filters.py _oneshot_filter; measured there: 3.5 ms -> 0.56 ms per repeated call).
+const ONESHOT_KEEP = 8
+oneshot_cache() = get!(() -> Vector{Pair{Any,Any}}(), task_local_storage(), :multirate_oneshot)::Vector{Pair{Any,Any}}
+
+function oneshot_filter(h::Vector, x::VecOrMat, args...)
+    cache = oneshot_cache()
+    key = (copy(h), args, eltype(x), size(x, 2))
+    i = findfirst(p -> isequal(p.first, key), cache)
+    if i === nothing
+        f = FIRFilter(h, args...)
+    else
+        f = cache[i].second
+        deleteat!(cache, i)
+        reset(f)
+    end
+    push!(cache, key => f)                                   # most recent last
+    length(cache) > ONESHOT_KEEP && popfirst!(cache)
+    return f
+end
+clear_oneshot_cache() = empty!(oneshot_cache())
+
+filt(h::Vector, x::VecOrMat, ratio::Rational = 1//1) = filt(oneshot_filter(h, x, ratio), x)
+filt(h::Vector, x::VecOrMat, rate::AbstractFloat, Nϕ::Integer = 32) = filt(oneshot_filter(h, x, rate, Nϕ), x)
+filt(h::Vector, x::VecOrMat, rate::AbstractFloat, Nϕ::Integer, polyorder::Integer) = filt(oneshot_filter(h, x, rate, Nϕ, polyorder), x)
 
 # ---- state, lengths, utilities ----------------------------------------------------------------------------------------
 # reset(self): src/Filters.jl:244-260, defined as full re-initialisation (SURVEY 9.2)
